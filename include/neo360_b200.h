@@ -1,0 +1,187 @@
+/*
+ * neo360_b200 -- C ABI of the B200-native NeO-360 ray-marching hot path.
+ *
+ * The reference (zubair-irshad/NeO-360) is pure Python; it has no FFI / operator registry.  The seam
+ * this library sits behind is the Python call `self.model(rays, randomized, white_bkgd, near, far,
+ * out_depth)` made by models/neo360/model.py:725-732, 841-843, 882-884.
+ * `neo360_b200/renderer.py` mirrors that call and binds the entry points below through ctypes;
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless marked HOST; the caller (PyTorch)
+ *     owns all buffers, the library borrows them for the duration of the call;
+ *   - the only library-owned object is the opaque NeoScene (re-laid-out feature maps + packed weights),
+ *     released with neo_scene_free;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); no call synchronises except
+ *     neo_scene_create (once per scene) and neo_check_async;
+ *   - return value 0 = ok, negative = NeoStatus; neo_last_error() gives the message (per thread);
+ *     nothing throws across the ABI.  One caller thread per process / GPU.
+ */
+#ifndef NEO360_B200_H
+#define NEO360_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    NEO_OK = 0,
+    NEO_ERR_INVALID = -1,   /* bad argument */
+    NEO_ERR_CUDA = -2,      /* CUDA runtime error, see neo_last_error */
+    NEO_ERR_WORKSPACE = -3, /* workspace too small */
+    NEO_ERR_GEOMETRY = -4,  /* a ray misses the unit sphere: the reference asserts (helper.py:271,426) */
+    NEO_ERR_UNSUPPORTED = -5
+} NeoStatus;
+
+/* arithmetic of the density/colour MLP */
+typedef enum {
+    NEO_PREC_FP32 = 0, /* CUDA-core fp32, reference formulation; tightest parity (debug / validation) */
+    NEO_PREC_TC = 1    /* tcgen05 tensor cores, 16-bit operands, fp32 accumulate (the fast path) */
+} NeoPrecision;
+
+/* One NeRFPPMLP (models/neo360/model.py:37-158).  nn.Linear layout: weight (out,in) row-major, bias (out). */
+typedef struct {
+    int in_ch;              /* 3 = fg (63-d pos-enc), 4 = bg (84-d) */
+    const float *w0, *b0;   /* pts_linears.0   (128, 63|84 + 512 + 128) */
+    const float *w1, *b1;   /* pts_linears.1   (128,128) */
+    const float *w2, *b2;   /* pts_linears.2   (128,128) */
+    const float *w3, *b3;   /* pts_linears.3   (128, 128 + 63|84 + 512 + 128) */
+    const float *wb, *bb;   /* bottleneck_layer (128,128) */
+    const float *wsig, *bsig; /* density_layer (1,128) */
+    const float *wv0, *bv0; /* views_linear.0  (64, 128+27) */
+    const float *wv1, *bv1; /* views_linear.1  (64,64) */
+    const float *wrgb, *brgb; /* rgb_layer     (3,64) */
+} NeoMLPParams;
+
+/* What the (out-of-scope) encoder produced for one scene + the source cameras.
+ * Replaces: encoder outputs consumed by index_grid (encoder_tp_fusion_conv.py:122-209) and
+ * SpatialEncoder.index (encoder_pn.py:101-152); rays["src_poses"|"src_focal"|"src_c"|"src_imgs"] of
+ * NeRF_TP.forward (model.py:266-274). */
+typedef struct {
+    int nv;                       /* number of source views (reference: 3) */
+    int plane_h, plane_w;         /* tri-plane size (reference: 120 x 160) */
+    int world_ch;                 /* 128 */
+    int lat_h, lat_w, local_ch;   /* pixel-aligned latent (reference: H/2, W/2, 512) */
+    int img_w, img_h;             /* src_imgs.shape[-1], [-2] (model.py:267-269) */
+    const float* planes_xz;       /* (nv, world_ch, plane_h, plane_w) NCHW */
+    const float* planes_xy;
+    const float* planes_yz;
+    const float* latent;          /* (nv, local_ch, lat_h, lat_w) NCHW */
+    const float* src_poses;       /* (nv,4,4) camera-to-world */
+    const float* src_focal;       /* (nv,)  only [0] is used (model.py:242) */
+    const float* src_c;           /* (nv,2) only [0] is used (model.py:244) */
+} NeoSceneDesc;
+
+typedef struct NeoScene NeoScene;
+
+/* Build the per-scene state: channel-last feature maps, R^T / -R^T t per view, MLP weights packed for
+ * the selected precision.  mlps[4] = {fg_coarse, bg_coarse, fg_fine, bg_fine} (model.py:215-237).
+ * `precision_mask` is a bit-or of (1<<NEO_PREC_FP32) | (1<<NEO_PREC_TC): which paths to prepare. */
+int neo_scene_create(const NeoSceneDesc* desc, const NeoMLPParams mlps[4], int precision_mask,
+                     NeoScene** out, void* stream);
+void neo_scene_free(NeoScene* scene);
+/* bytes of device memory held by the scene */
+size_t neo_scene_bytes(const NeoScene* scene);
+
+/* rays of one call: rays["rays_o"|"rays_d"|"viewdirs"] (nerds360_ae.py:1007-1023). */
+typedef struct {
+    int n_rays;
+    int chunk;               /* the reference's --chunk (opt.py:195-200): rays are conditioned on the view
+                                direction of ray ((b*N+s) mod B) of their own chunk (quirk Q1, model.py:358-360);
+                                chunk <= 0 means one chunk = n_rays (what a direct model(...) call does) */
+    const float* rays_o;     /* (n_rays,3) */
+    const float* rays_d;     /* (n_rays,3) */
+    const float* viewdirs;   /* (n_rays,3) */
+} NeoRays;
+
+typedef struct {
+    int n_coarse;            /* NeRF_TP.num_coarse_samples (level 0 evaluates n_coarse+1 points, quirk Q6) */
+    int n_fine;              /* NeRF_TP.num_fine_samples   (level 1 evaluates n_coarse+1+n_fine points) */
+    int white_bkgd;          /* only honoured when out_depth == 0 (model.py:501,519 vs 551,560) */
+    int out_depth;           /* 1: eval tuple, 0: train tuple */
+    int precision;           /* NeoPrecision */
+    /* randomized=True: uniforms the reference would draw with torch.rand (helper.py:50,199); NULL = deterministic */
+    const float* u_fg0;      /* (n_rays, n_coarse+1) */
+    const float* u_bg0;      /* (n_rays, n_coarse+1) */
+    const float* u_fg1;      /* (n_rays, n_fine) */
+    const float* u_bg1;      /* (n_rays, n_fine) */
+} NeoCfg;
+
+/* Per level l in {0,1}; N_l = n_coarse+1 (+ n_fine).  NULL pointers are skipped.
+ * eval tuple  (model.py:525-527): comp_rgb, fg_rgb, bg_rgb, fg_acc, bg_lambda, depth
+ * train tuple (model.py:577-579): comp_rgb, fg_w, bg_w, fg_sdist, bg_sdist, bg_acc */
+typedef struct {
+    float* comp_rgb[2];   /* (n_rays,3) */
+    float* fg_rgb[2];     /* (n_rays,3) */
+    float* bg_rgb[2];     /* (n_rays,3) */
+    float* fg_acc[2];     /* (n_rays)   */
+    float* bg_lambda[2];  /* (n_rays,1) */
+    float* depth[2];      /* (n_rays)   */
+    float* bg_acc[2];     /* (n_rays)   */
+    float* fg_w[2];       /* (n_rays,N_l) */
+    float* bg_w[2];       /* (n_rays,N_l) */
+    float* fg_sdist[2];   /* (n_rays,N_l) */
+    float* bg_sdist[2];   /* (n_rays,N_l) */
+    /* optional debug taps (parity tests): per-sample values of level l */
+    float* fg_t[2];       /* (n_rays,N_l) */
+    float* bg_s[2];       /* (n_rays,N_l) */
+    float* fg_sigma[2];   /* (n_rays,N_l) */
+    float* bg_sigma[2];   /* (n_rays,N_l) */
+    float* fg_rgb_s[2];   /* (n_rays,N_l,3) */
+    float* bg_rgb_s[2];   /* (n_rays,N_l,3) */
+} NeoOut;
+
+/* Workspace (device) the caller must provide to neo_render_fwd for n_rays rays. */
+size_t neo_render_workspace_bytes(int n_rays, const NeoCfg* cfg);
+
+/* NeRF_TP.forward with the encoder hoisted (model.py:266-581 minus :272-274).  Replaces the call at
+ * model.py:725-732 / 841-843 / 882-884. */
+int neo_render_fwd(const NeoScene* scene, const NeoRays* rays, const NeoCfg* cfg, NeoOut* out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Synchronise `stream` and report deferred device-side errors (the reference's two asserts,
+ * helper.py:271,426, are host syncs; here they are a flag checked on demand). */
+int neo_check_async(const NeoScene* scene, void* stream);
+
+/* ---- stage-level entry points (mirror the reference helpers one to one; used by the parity tests) ---- */
+
+/* datasets/ray_utils.py:84-104 + 133-176: pixel grid + c2w (3,4 row-major, device) -> rays. */
+int neo_get_rays(int H, int W, float focal, const float* c2w, float* rays_o, float* viewdirs, float* rays_d,
+                 float* radii, void* stream);
+/* models/neo360/helper.py:253-273 */
+int neo_intersect_sphere(const float* rays_o, const float* rays_d, int n_rays, float* far, int* err_flag,
+                         void* stream);
+/* models/neo360/helper.py:24-75.  in_sphere=1: t (n,N+1), pts (n,N+1,3).  in_sphere=0: t=s (n,N+1) descending,
+ * pts (n,N+1,4), pts_linear (n,N+1,3).  u_rand NULL = deterministic. */
+int neo_sample_along_rays(const float* rays_o, const float* rays_d, const float* far, int n_rays, int num_samples,
+                          int in_sphere, float far_uncontracted, const float* u_rand, float* t_vals, float* pts,
+                          float* pts_linear, void* stream);
+/* models/neo360/helper.py:218-249 (sorted_piecewise_constant_pdf 174-215 inside): bins=mids(t_old), weights[1:-1]. */
+int neo_sample_pdf(const float* rays_o, const float* rays_d, const float* far, const float* t_old,
+                   const float* weights, int n_rays, int n_old, int num_samples, int in_sphere,
+                   float far_uncontracted, const float* u_rand, float* t_vals, float* pts, float* pts_linear,
+                   void* stream);
+/* models/neo360/helper.py:128-171.  rgb (n,N,3), sigma (n,N), t (n,N). */
+int neo_volumetric_rendering(const float* rgb, const float* sigma, const float* t_vals, const float* rays_d,
+                             const float* far, int n_rays, int N, int white_bkgd, int in_sphere, float* comp_rgb,
+                             float* acc, float* weights, float* bg_lambda, float* depth, void* stream);
+/* encoder_tp_fusion_conv.py:122-209: pts (M,3) world -> (nv*M,128), rows ordered (view, point). */
+int neo_index_grid(const NeoScene* scene, const float* pts, int M, float* out, void* stream);
+/* model.py:239-264 (get_local_feats): pts (M,3) world -> (nv*M,512). */
+int neo_index_local(const NeoScene* scene, const float* pts, int M, float* out, void* stream);
+/* `predict` (model.py:343-407) for one branch of one level: t/s (n,N) -> rgb (n,N,3), sigma (n,N).
+ * mlp_index in 0..3 = {fg_coarse,bg_coarse,fg_fine,bg_fine}; is_bg selects the NeRF++ background parametrisation. */
+int neo_field_eval(const NeoScene* scene, const NeoRays* rays, const float* far, const float* t_vals, int N,
+                   int mlp_index, int precision, float* rgb, float* sigma, void* stream);
+
+const char* neo_last_error(void);
+/* "neo360_b200 <version> sm_100a" */
+const char* neo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEO360_B200_H */

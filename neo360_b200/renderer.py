@@ -1,0 +1,277 @@
+"""Drop-in for the reference's NeO-360 renderer behind its own call surface.
+
+    reference                                         here
+    ---------------------------------------------     ------------------------------------------------
+    models/neo360/model.py:37   NeRFPPMLP             NeRFPPMLP  (same parameter names / shapes; weights only)
+    models/neo360/model.py:162  NeRF_TP               NeRF_TP    (same ctor args, same forward signature + returns)
+    model.py:861-907 render_rays_test chunk loop      NeRF_TP.render_rays_test(batch, chunk)  (one call, same result)
+
+`forward(rays, randomized, white_bkgd, near, far, out_depth=False)` returns the reference's `list[2]` of tuples
+(model.py:525-527 / 577-579).  The encoder (GridEncoder, out of scope: SURVEY.md section 8(f1)) is hoisted out of the
+chunk loop (quirk Q5): call `set_scene(...)` once per scene with its outputs, or pass them in the `rays` dict under
+`planes_xz|planes_xy|planes_yz|latent`; or hand an `encoder` module to the constructor and it is run once per new set
+of `src_*` tensors.  All arithmetic runs in libneo360_b200.so (hand-written CUDA, sm_100a); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+PRECISIONS = {"fp32": L.NEO_PREC_FP32, "tc": L.NEO_PREC_TC}
+
+
+class NeRFPPMLP(nn.Module):
+    """Parameter container with the reference's layout (models/neo360/model.py:37-108).  Evaluation happens in CUDA."""
+
+    def __init__(self, min_deg_point, max_deg_point, deg_view, netdepth: int = 4, netwidth: int = 128,
+                 netdepth_condition: int = 2, netwidth_condition: int = 64, skip_layer: int = 2, input_ch: int = 3,
+                 input_ch_view: int = 3, num_rgb_channels: int = 3, num_density_channels: int = 1,
+                 local_latent_size: int = 512, world_latent_size: int = 128, combine_layer: int = 3,
+                 combine_type="average", out_nocs=False, num_src_views=3):
+        super().__init__()
+        if (netdepth, netwidth, netdepth_condition, netwidth_condition, skip_layer, combine_layer, combine_type,
+                local_latent_size, world_latent_size, out_nocs) != (4, 128, 2, 64, 2, 3, "average", 512, 128, False):
+            raise NotImplementedError("the CUDA path implements the reference's default NeRFPPMLP architecture")
+        if (min_deg_point, max_deg_point, deg_view) != (0, 10, 4) or input_ch not in (3, 4):
+            raise NotImplementedError("pos-enc degrees are fixed to the reference's (0,10,4)")
+        self.input_ch = input_ch
+        pos = ((max_deg_point - min_deg_point) * 2 + 1) * input_ch + local_latent_size + world_latent_size
+        view = (deg_view * 2 + 1) * input_ch_view
+        layers = [nn.Linear(pos, netwidth)]
+        for idx in range(netdepth - 1):
+            layers.append(nn.Linear(netwidth + pos if (idx % skip_layer == 0 and idx > 0) else netwidth, netwidth))
+        self.pts_linears = nn.ModuleList(layers)
+        self.views_linear = nn.ModuleList([nn.Linear(netwidth + view, netwidth_condition),
+                                           nn.Linear(netwidth_condition, netwidth_condition)])
+        self.bottleneck_layer = nn.Linear(netwidth, netwidth)
+        self.density_layer = nn.Linear(netwidth, num_density_channels)
+        self.rgb_layer = nn.Linear(netwidth_condition, num_rgb_channels)
+        for m in list(self.pts_linears) + [self.views_linear[1], self.bottleneck_layer, self.density_layer, self.rgb_layer]:
+            nn.init.xavier_uniform_(m.weight)
+
+    def c_params(self, keep: list) -> L.NeoMLPParams:
+        p = L.NeoMLPParams()
+        p.in_ch = self.input_ch
+
+        def put(wn, bn, lin):
+            w, b = lin.weight.detach().contiguous().float(), lin.bias.detach().contiguous().float()
+            keep.extend([w, b])
+            setattr(p, wn, L.ptr(w)); setattr(p, bn, L.ptr(b))
+
+        for i in range(4):
+            put(f"w{i}", f"b{i}", self.pts_linears[i])
+        put("wb", "bb", self.bottleneck_layer)
+        put("wsig", "bsig", self.density_layer)
+        put("wv0", "bv0", self.views_linear[0])
+        put("wv1", "bv1", self.views_linear[1])
+        put("wrgb", "brgb", self.rgb_layer)
+        return p
+
+    def forward(self, *a, **k):
+        raise RuntimeError("NeRFPPMLP is evaluated inside the fused CUDA path; call NeRF_TP.forward")
+
+
+class Scene:
+    """Owns a NeoScene handle (re-laid-out feature maps + packed weights) for one scene + parameter version."""
+
+    def __init__(self, handle, nbytes):
+        self.handle = handle
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().neo_scene_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class NeRF_TP(nn.Module):
+    def __init__(self, num_levels: int = 2, min_deg_point: int = 0, max_deg_point: int = 10, deg_view: int = 4,
+                 num_coarse_samples: int = 128, num_fine_samples: int = 256, use_viewdirs: bool = True,
+                 num_src_views: int = 3, density_noise: float = 0.0, lindisp: bool = False, encoder: Optional[nn.Module] = None,
+                 precision: str = "tc", chunk: Optional[int] = None, **unused):
+        super().__init__()
+        if num_levels != 2 or lindisp or density_noise != 0.0 or not use_viewdirs:
+            raise NotImplementedError("reference defaults only: 2 levels, lindisp=False, density_noise=0 (model.py:165-175)")
+        self.num_coarse_samples, self.num_fine_samples, self.num_src_views = num_coarse_samples, num_fine_samples, num_src_views
+        self.precision = precision
+        self.chunk = chunk
+        self.encoder = encoder
+        mk = lambda ch: NeRFPPMLP(min_deg_point, max_deg_point, deg_view, num_src_views=num_src_views, input_ch=ch)
+        self.fg_coarse_mlp, self.fg_fine_mlp = mk(3), mk(3)
+        self.bg_coarse_mlp, self.bg_fine_mlp = mk(4), mk(4)
+        self._scene: Optional[Scene] = None
+        self._scene_key = None
+        self._ws = None
+
+    # ---- scene handling (encoder hoisted, quirk Q5) ----
+    def _mlps(self):
+        return [self.fg_coarse_mlp, self.bg_coarse_mlp, self.fg_fine_mlp, self.bg_fine_mlp]
+
+    def set_scene(self, planes_xz, planes_xy, planes_yz, latent, src_poses, src_focal, src_c, img_wh, precisions=None):
+        lib = L.load()
+        dev = planes_xz.device
+        if dev.type != "cuda":
+            raise RuntimeError("neo360_b200 needs CUDA tensors (no CPU fallback)")
+        keep = []
+        f = lambda t: (keep.append(t.detach().contiguous().float()) or keep[-1])
+        d = L.NeoSceneDesc()
+        d.nv, d.world_ch, d.plane_h, d.plane_w = planes_xz.shape
+        _, d.local_ch, d.lat_h, d.lat_w = latent.shape
+        d.img_w, d.img_h = int(img_wh[0]), int(img_wh[1])
+        d.planes_xz, d.planes_xy, d.planes_yz = L.ptr(f(planes_xz)), L.ptr(f(planes_xy)), L.ptr(f(planes_yz))
+        d.latent = L.ptr(f(latent))
+        d.src_poses, d.src_focal, d.src_c = L.ptr(f(src_poses)), L.ptr(f(src_focal)), L.ptr(f(src_c))
+        arr = (L.NeoMLPParams * 4)(*[m.to(dev).c_params(keep) for m in self._mlps()])
+        precisions = precisions or [self.precision]
+        mask = 0
+        for p in precisions:
+            mask |= 1 << PRECISIONS[p]
+        h = C.c_void_p()
+        L.check(lib.neo_scene_create(C.byref(d), arr, mask, C.byref(h), torch.cuda.current_stream().cuda_stream))
+        self._scene = Scene(h, lib.neo_scene_bytes(h))
+        return self._scene
+
+    def _ensure_scene(self, rays):
+        if all(k in rays for k in ("planes_xz", "planes_xy", "planes_yz", "latent")):
+            key = tuple((rays[k].data_ptr(), rays[k]._version) for k in ("planes_xz", "latent", "src_poses"))
+            if key != self._scene_key:
+                W, H = rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2]
+                self.set_scene(rays["planes_xz"], rays["planes_xy"], rays["planes_yz"], rays["latent"], rays["src_poses"],
+                               rays["src_focal"], rays["src_c"], (W, H))
+                self._scene_key = key
+        elif self.encoder is not None and "src_imgs" in rays:
+            key = tuple((rays[k].data_ptr(), rays[k]._version) for k in ("src_imgs", "src_poses"))
+            if key != self._scene_key:
+                with torch.no_grad():
+                    xz, xy, yz = self.encoder(rays["src_imgs"], rays["src_poses"], rays["src_focal"], rays["src_c"])
+                    latent = self.encoder.spatial_encoder.latent
+                W, H = rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2]
+                self.set_scene(xz, xy, yz, latent, rays["src_poses"], rays["src_focal"], rays["src_c"], (W, H))
+                self._scene_key = key
+        if self._scene is None:
+            raise RuntimeError("no scene: call set_scene(...) or pass planes_*/latent in `rays`, or give an encoder")
+        return self._scene
+
+    # ---- the reference's call surface ----
+    def forward(self, rays: Dict[str, torch.Tensor], randomized: bool, white_bkgd: bool, near=None, far=None,
+                out_depth: bool = False, chunk: Optional[int] = None, debug: bool = False) -> List[tuple]:
+        """near/far are ignored exactly as the reference ignores them (quirk Q4, model.py:277-278)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("backward through the fused CUDA path is not built yet (SURVEY.md 8(f2)); "
+                                      "call under torch.no_grad() / .eval()")
+        lib = L.load()
+        sc = self._ensure_scene(rays)
+        o = rays["rays_o"].contiguous().float()
+        d = rays["rays_d"].contiguous().float()
+        vd = rays["viewdirs"].contiguous().float()
+        if not o.is_cuda:
+            raise RuntimeError("neo360_b200 needs CUDA tensors (no CPU fallback)")
+        n, dev = o.shape[0], o.device
+        nc, nf = self.num_coarse_samples, self.num_fine_samples
+        N = (nc + 1, nc + 1 + nf)
+        cfg = L.NeoCfg()
+        cfg.n_coarse, cfg.n_fine = nc, nf
+        cfg.white_bkgd, cfg.out_depth = int(bool(white_bkgd)), int(bool(out_depth))
+        cfg.precision = PRECISIONS[self.precision]
+        keep = []
+        if randomized:
+            # same draw order and shapes as the reference: helper.py:50 (fg, bg) then helper.py:199 (fg, bg)
+            u = [torch.rand((n, nc + 1), device=dev), torch.rand((n, nc + 1), device=dev),
+                 torch.rand((n, nf), device=dev), torch.rand((n, nf), device=dev)]
+            u = rays.get("_uniforms", u)
+            keep.extend(u)
+            cfg.u_fg0, cfg.u_bg0, cfg.u_fg1, cfg.u_bg1 = [L.ptr(x.contiguous()) for x in u]
+        r = L.NeoRays()
+        r.n_rays = n
+        r.chunk = int(chunk if chunk is not None else (self.chunk or 0))
+        r.rays_o, r.rays_d, r.viewdirs = L.ptr(o), L.ptr(d), L.ptr(vd)
+        need = lib.neo_render_workspace_bytes(n, C.byref(cfg))
+        if need == 0:
+            raise RuntimeError("neo360_b200: " + lib.neo_last_error().decode())
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out = L.NeoOut()
+        T: Dict[str, list] = {}
+
+        def want(name, *shape_fn):
+            T[name] = []
+            for lvl in range(2):
+                t = torch.empty(*[s(lvl) if callable(s) else s for s in shape_fn], device=dev)
+                T[name].append(t)
+                getattr(out, name)[lvl] = t.data_ptr()
+
+        NL = lambda lvl: N[lvl]
+        want("comp_rgb", n, 3)
+        if out_depth:
+            want("fg_rgb", n, 3); want("bg_rgb", n, 3); want("fg_acc", n); want("bg_lambda", n, 1); want("depth", n)
+        else:
+            want("fg_w", n, NL); want("bg_w", n, NL); want("fg_sdist", n, NL); want("bg_sdist", n, NL); want("bg_acc", n)
+        if debug:
+            for k in ("fg_t", "bg_s", "fg_sigma", "bg_sigma"):
+                want(k, n, NL)
+            want("fg_rgb_s", n, NL, 3); want("bg_rgb_s", n, NL, 3)
+            if out_depth:
+                want("fg_w", n, NL); want("bg_w", n, NL)
+        L.check(lib.neo_render_fwd(sc.handle, C.byref(r), C.byref(cfg), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
+                                   torch.cuda.current_stream().cuda_stream))
+        ret = []
+        for lvl in range(2):
+            if out_depth:
+                ret.append(tuple(T[k][lvl] for k in ("comp_rgb", "fg_rgb", "bg_rgb", "fg_acc", "bg_lambda", "depth")))
+            else:
+                ret.append(tuple(T[k][lvl] for k in ("comp_rgb", "fg_w", "bg_w", "fg_sdist", "bg_sdist", "bg_acc")))
+        if debug:
+            self.last_debug = T
+        return ret
+
+    # ---- stage-level operators that need the scene (parity tests) ----
+    def index_grid(self, samples: torch.Tensor) -> torch.Tensor:
+        """encoder_tp_fusion_conv.py:122-209: samples (...,3) world -> (NV*M,128), rows ordered (view, point)."""
+        pts = samples.reshape(-1, 3).contiguous().float()
+        out = torch.empty(self.num_src_views * pts.shape[0], 128, device=pts.device)
+        L.check(L.load().neo_index_grid(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
+                                        torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def get_local_feats(self, samples: torch.Tensor) -> torch.Tensor:
+        """model.py:239-264: samples (...,3) world -> (NV*M,512)."""
+        pts = samples.reshape(-1, 3).contiguous().float()
+        out = torch.empty(self.num_src_views * pts.shape[0], 512, device=pts.device)
+        L.check(L.load().neo_index_local(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
+                                         torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def field_eval(self, rays, far, t_vals, mlp_index: int, chunk: int = 0, precision: Optional[str] = None):
+        """`predict` (model.py:343-407) of one branch: t/s (n,N) -> rgb (n,N,3), sigma (n,N,1)."""
+        o, d, vd = (rays[k].contiguous().float() for k in ("rays_o", "rays_d", "viewdirs"))
+        t = t_vals.contiguous().float()
+        fr = far.reshape(-1).contiguous().float()
+        n, N = t.shape
+        r = L.NeoRays()
+        r.n_rays, r.chunk = n, int(chunk)
+        r.rays_o, r.rays_d, r.viewdirs = L.ptr(o), L.ptr(d), L.ptr(vd)
+        rgb = torch.empty(n, N, 3, device=t.device)
+        sig = torch.empty(n, N, 1, device=t.device)
+        L.check(L.load().neo_field_eval(self._scene.handle, C.byref(r), L.ptr(fr), L.ptr(t), N, mlp_index,
+                                        PRECISIONS[precision or self.precision], L.ptr(rgb), L.ptr(sig),
+                                        torch.cuda.current_stream().cuda_stream))
+        return rgb, sig
+
+    def check(self):
+        """Synchronise and surface deferred device-side errors (the reference's asserts, helper.py:271,426)."""
+        L.check(L.load().neo_check_async(self._scene.handle, torch.cuda.current_stream().cuda_stream))
+
+    @torch.no_grad()
+    def render_rays_test(self, batch: Dict[str, torch.Tensor], chunk: int = 1024, white_bkgd: bool = False):
+        """models/neo360/model.py:861-907 without the Python chunk loop: one call over every ray of the frame; the
+        reference's per-chunk view-direction conditioning (quirk Q1) is reproduced from `chunk`."""
+        out = self.forward(batch, False, white_bkgd, None, None, out_depth=True, chunk=chunk)[1]
+        return {"rgb": out[0], "fg_rgb": out[1], "bg_rgb": out[2], "depth": out[5], "fg_acc": out[3]}

@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs and against the golden
+vectors minted from the unmodified reference.  Tolerances are stated per test.  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+from neo360_b200 import synth
+from oracle import neo360_oracle as orc
+
+pytestmark = pytest.mark.gpu
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from neo360_b200 import build
+    build.build()
+    return torch.device("cuda:0")
+
+
+def md(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def rays_in_sphere(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = (torch.rand(n, 3, generator=g) - 0.5) * 1.1
+    d = torch.randn(n, 3, generator=g)
+    return o, d / d.norm(dim=-1, keepdim=True)
+
+
+# ---------------- stage-level parity (bit-level or few-ulp) ----------------
+
+def test_get_rays(cuda):
+    from neo360_b200 import ops
+    pose = synth.target_pose(7, 100)
+    for (H, W) in ((6, 8), (48, 64), (480, 640)):
+        o, vd, rd, rad = ops.get_rays(H, W, 0.8 * W, pose.to(cuda))
+        ro, rvd, rrd, rrad = orc.rays_from_pose(orc.ray_directions(H, W, 0.8 * W), pose[:3, :4])
+        assert md(o, ro) == 0 and md(vd, rvd) < 2e-7 and md(rd, rrd) < 2e-7 and md(rad, rrad) < 1e-9
+
+
+def test_intersect_and_coarse_sampling(cuda, golden):
+    from neo360_b200 import ops
+    o, d = T(golden["kat_o"]), T(golden["kat_d"])
+    far = ops.intersect_sphere(o.to(cuda), d.to(cuda))
+    assert md(far, T(golden["kat_far"])) <= 2.4e-7          # <= 2 ulp at ~1
+    farc = T(golden["kat_far"]).to(cuda)
+    near = torch.full_like(farc, 1e-4)
+    t, p = ops.sample_along_rays(o.to(cuda), d.to(cuda), 4, near, farc, False, False, True)
+    assert md(t, T(golden["kat_fg_t"])) == 0 and md(p, T(golden["kat_fg_p"])) == 0
+    s, bp, bl = ops.sample_along_rays(o.to(cuda), d.to(cuda), 4, near, farc, False, False, False, far_uncontracted=3)
+    assert md(s, T(golden["kat_bg_s"])) == 0 and md(bl, T(golden["kat_bg_l"])) == 0
+    assert md(bp, T(golden["kat_bg_p"])) < 2e-6          # asin/sin/cos differ by ulps between libm and CUDA
+    u = T(golden["kat_u"]).to(cuda)
+    tr, _ = ops.sample_along_rays(o.to(cuda), d.to(cuda), 4, near, farc, True, False, True, u_rand=u)
+    sr, _, lr = ops.sample_along_rays(o.to(cuda), d.to(cuda), 4, near, farc, True, False, False, 3, u_rand=u)
+    assert md(tr, T(golden["kat_fg_t_rand"])) == 0 and md(sr, T(golden["kat_bg_s_rand"])) == 0
+    assert md(lr, T(golden["kat_bg_l_rand"])) == 0
+    # larger seeded case against the oracle, n_coarse = 128 (config 2)
+    o, d = rays_in_sphere(4096, 3)
+    far = orc.intersect_sphere(o, d)
+    assert md(ops.intersect_sphere(o.to(cuda), d.to(cuda)), far) <= 4e-7
+    t, p = ops.sample_along_rays(o.to(cuda), d.to(cuda), 128, None, far.to(cuda), False, False, True)
+    t2, p2 = orc.sample_fg(o, d, 128, torch.full_like(far, 1e-4), far)
+    assert md(t, t2) == 0 and md(p, p2) == 0
+    with pytest.raises(AssertionError):                  # helper.py:271
+        ops.intersect_sphere(torch.tensor([[2.0, 0, 0]], device=cuda), torch.tensor([[0.0, 1, 0]], device=cuda))
+
+
+def test_volumetric_rendering(cuda, golden):
+    from neo360_b200 import ops
+    g = golden
+    rgb, sig, d = T(g["kat_rgb"]).to(cuda), T(g["kat_sig"]).to(cuda), T(g["kat_d"]).to(cuda)
+    fc = ops.volumetric_rendering(rgb, sig, T(g["kat_fg_t"]).to(cuda), d, False, True, t_far=T(g["kat_far"]).to(cuda), out_depth=True)
+    for a, k in zip(fc, ("kat_fg_comp", "kat_fg_acc", "kat_fg_w", "kat_fg_lam", "kat_fg_depth")):
+        assert md(a, T(g[k])) < 3e-7, k
+    bc = ops.volumetric_rendering(rgb, sig, T(g["kat_bg_s"]).to(cuda), d, False, False, out_depth=True)
+    for a, k in zip((bc[0], bc[1], bc[2], bc[4]), ("kat_bg_comp", "kat_bg_acc", "kat_bg_w", "kat_bg_depth")):
+        assert md(a, T(g[k])) < 3e-7, k
+    # config-2 length (193 samples), white background, against the oracle
+    gen = torch.Generator().manual_seed(5)
+    n, N = 2048, 193
+    o, dd = rays_in_sphere(n, 11)
+    far = orc.intersect_sphere(o, dd)
+    t = torch.sort(torch.rand(n, N, generator=gen), -1).values * far
+    rgb = torch.rand(n, N, 3, generator=gen)
+    sig = torch.rand(n, N, 1, generator=gen) * 8
+    ref = orc.composite(rgb, sig, t, dd, True, True, far)
+    got = ops.volumetric_rendering(rgb.to(cuda), sig.to(cuda), t.to(cuda), dd.to(cuda), True, True, t_far=far.to(cuda), out_depth=True)
+    for a, b in zip(got, ref):
+        assert md(a, b) < 2e-6
+    # size-independent properties: weights >= 0, sum(w) == acc, acc + lambda == 1 (up to the 1e-10 eps, quirk Q9)
+    comp, acc, w, lam, _ = got
+    assert float(w.min()) >= 0 and md(w.sum(-1), acc) < 1e-5 and md(acc + lam[:, 0], torch.ones(n)) < 1e-4
+
+
+def test_sample_pdf(cuda, golden):
+    from neo360_b200 import ops
+    g = golden
+    o, d, far = T(g["kat_o"]).to(cuda), T(g["kat_d"]).to(cuda), T(g["kat_far"]).to(cuda)
+    # fg: t = sort(t_old U invCDF)
+    t_old, w = T(g["kat_fg_t"]), T(g["kat_fg_w"])
+    exp = torch.sort(torch.cat([t_old, T(g["kat_pdf_fg"])], -1), -1).values
+    t, p = ops.sample_pdf(t_old.to(cuda), w.to(cuda), o, d, 6, False, True, far)
+    assert md(t, exp) < 2e-7
+    exp_r = torch.sort(torch.cat([t_old, T(g["kat_pdf_rand"])], -1), -1).values
+    t, _ = ops.sample_pdf(t_old.to(cuda), w.to(cuda), o, d, 6, True, True, far, u_rand=T(g["kat_u6"]).to(cuda))
+    assert md(t, exp_r) < 2e-7
+    # bg: descending bins (quirk Q17), output flipped to descending
+    s_old, wb = T(g["kat_bg_s"]), T(g["kat_bg_w"])
+    exp_b = torch.flip(torch.sort(torch.cat([s_old, T(g["kat_pdf_bg"])], -1), -1).values, dims=[-1])
+    s, bp, bl = ops.sample_pdf(s_old.to(cuda), wb.to(cuda), o, d, 6, False, False, far, 3.0)
+    assert md(s, exp_b) < 2e-7
+    # config-2 sizes vs oracle: 129 old + 64 new.  The inverse CDF is discontinuous in the bg case, so compare
+    # robustly: all but a handful of samples within 1e-6, every sample inside [0,1] and sorted.
+    n = 2048
+    oo, dd = rays_in_sphere(n, 21)
+    fr = orc.intersect_sphere(oo, dd)
+    t0, _ = orc.sample_fg(oo, dd, 128, torch.full_like(fr, 1e-4), fr)
+    gen = torch.Generator().manual_seed(2)
+    wts = torch.rand(n, 129, generator=gen) ** 4
+    wts[::7] *= 1e-9                                         # exercises the 1e-5 padding branch (helper.py:178-182)
+    t_ref, _ = orc.resample_fg(oo, dd, t0, wts, 64)
+    t_got, p_got = ops.sample_pdf(t0.to(cuda), wts.to(cuda), oo.to(cuda), dd.to(cuda), 64, False, True, fr.to(cuda))
+    assert md(t_got, t_ref) < 2e-6
+    assert bool((t_got[:, 1:] >= t_got[:, :-1]).all())
+    s0, _, _ = orc.sample_bg(oo, dd, 128, fr)
+    s_ref, bp_ref, bl_ref = orc.resample_bg(oo, dd, s0, wts, 64, fr)
+    s_got, bp_got, bl_got = ops.sample_pdf(s0.to(cuda), wts.to(cuda), oo.to(cuda), dd.to(cuda), 64, False, False, fr.to(cuda), 3.0)
+    bad = ((s_got.cpu() - s_ref).abs() > 2e-6).float().mean()
+    assert float(bad) < 1e-3, float(bad)
+    assert bool((s_got[:, 1:] <= s_got[:, :-1]).all()) and float(s_got.min()) >= 0 and float(s_got.max()) <= 1
+
+
+# ---------------- scene-dependent stages ----------------
+
+def make_net(cuda, img_wh, plane_hw, nc, nf, seed, precisions=("fp32",), precision="fp32"):
+    from neo360_b200 import NeRF_TP
+    sc = synth.make_scene(img_wh, 3, plane_hw, seed)
+    P = synth.make_mlp_params(seed)
+    net = NeRF_TP(num_coarse_samples=nc, num_fine_samples=nf, precision=precision).eval()
+    net.load_state_dict(P)
+    net = net.to(cuda)
+    net.set_scene(*[sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")],
+                  sc["img_wh"], precisions=list(precisions))
+    W, H = img_wh
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+    return net, osc, P
+
+
+def test_feature_lookups(cuda):
+    net, osc, P = make_net(cuda, (64, 48), (24, 32), 8, 4, 0)
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(3000, 3, generator=g) - 0.5) * 3.0          # includes points that project outside -> zeros padding
+    cam = orc.world2camera(pts, osc.src_poses)
+    ref_w = orc.triplane_lookup(cam, osc).reshape(-1, 128)
+    ref_l = orc.local_lookup(cam, osc).reshape(-1, 512)
+    assert md(net.index_grid(pts.to(cuda)), ref_w) < 2e-5
+    got_l = net.get_local_feats(pts.to(cuda))
+    # projection through -x/(z+1e-9) amplifies ulps near z=0; compare where the reference coordinate is well conditioned
+    ok = (cam[..., 2].abs() > 1e-2).reshape(-1)
+    assert md(got_l.cpu()[ok], ref_l[ok]) < 5e-4
+
+
+def test_field_eval_fp32_vs_oracle(cuda):
+    nc = 16
+    net, osc, P = make_net(cuda, (64, 48), (24, 32), nc, 8, 0)
+    pose = synth.target_pose(3, 100)
+    ro, vd, rd, _ = orc.rays_from_pose(orc.ray_directions(48, 64, 0.8 * 64), pose[:3, :4])
+    sel = slice(1000, 1000 + 40)
+    rays = {"rays_o": ro[sel].contiguous(), "rays_d": rd[sel].contiguous(), "viewdirs": vd[sel].contiguous()}
+    with torch.no_grad():
+        _, aux = orc.render(rays, osc, P, nc, 8, False, True, return_aux=True)
+    cr = {k: v.to(cuda) for k, v in rays.items()}
+    for lvl in range(2):
+        for b, (tk, rk, sk) in enumerate((("fg_t", "fg_rgb", "fg_sigma"), ("bg_s", "bg_rgb", "bg_sigma"))):
+            rgb, sig = net.field_eval(cr, aux[lvl]["far"].to(cuda), aux[lvl][tk].to(cuda), 2 * lvl + b, precision="fp32")
+            assert md(sig, aux[lvl][sk]) < 5e-5, (lvl, b)
+            assert md(rgb, aux[lvl][rk]) < 5e-5, (lvl, b)
+
+
+EV = ("comp_rgb", "fg_rgb", "bg_rgb", "fg_acc", "bg_lambda", "depth")
+TR = ("comp_rgb", "fg_w", "bg_w", "fg_sdist", "bg_sdist", "bg_acc")
+
+
+@pytest.mark.parametrize("tag", ["tiny", "small"])
+def test_end_to_end_fp32_vs_reference_vectors(cuda, golden, tag):
+    """NEO_PREC_FP32 against outputs of the UNMODIFIED reference (tests/golden).  Tolerance: 2e-4 abs on every output
+    (fp32 re-association through the gained MLP); bg resampling is discontinuous at CDF bracket edges (quirk Q17), so
+    the randomized/bg cases allow 1e-3 on <=1% of entries."""
+    g = golden
+    W, H, hp, wp, B, nc, nf, seed, start = [int(x) for x in g[f"{tag}_cfg"]]
+    net, osc, P = make_net(cuda, (W, H), (hp, wp), nc, nf, seed)
+    rays = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs")}
+    with torch.no_grad():
+        ev = net(rays, False, False, 0.2, 3.0, out_depth=True)
+        tr = net(rays, False, True, 0.2, 3.0, out_depth=False)
+        rays_r = dict(rays)
+        rays_r["_uniforms"] = [T(g[f"{tag}_u_{k}"]).to(cuda) for k in ("fg0", "bg0", "fg1", "bg1")]
+        rr = net(rays_r, True, False, 0.2, 3.0, out_depth=True)
+    net.check()
+
+    def close(v, ref, name):
+        diff = (v.cpu().double() - T(ref).double()).abs()
+        assert float(diff.max()) < 1e-3, (name, float(diff.max()))
+        assert float((diff > 2e-4).double().mean()) <= 0.01, (name, float(diff.max()))
+
+    for lvl in range(2):
+        for n_, v in zip(EV, ev[lvl]):
+            close(v, g[f"{tag}_eval{lvl}_{n_}"], ("eval", lvl, n_))
+        for n_, v in zip(TR, tr[lvl]):
+            close(v, g[f"{tag}_train{lvl}_{n_}"], ("train", lvl, n_))
+        for n_, v in zip(EV, rr[lvl]):
+            close(v, g[f"{tag}_rand{lvl}_{n_}"], ("rand", lvl, n_))
+
+
+def test_chunked_frame_matches_oracle_chunk_loop(cuda):
+    """render_rays_test semantics: one call over a frame with chunk=C must equal the reference's Python loop over
+    C-ray chunks (quirk Q1 makes the result depend on C).  48x36 frame = 1728 rays, chunk 512 (last chunk ragged)."""
+    W, H, nc, nf = 48, 36, 24, 12
+    net, osc, P = make_net(cuda, (W, H), (24, 32), nc, nf, 2)
+    pose = synth.target_pose(11, 100)
+    ro, vd, rd, _ = orc.rays_from_pose(orc.ray_directions(H, W, 0.8 * W), pose[:3, :4])
+    rays = {"rays_o": ro, "rays_d": rd, "viewdirs": vd}
+    with torch.no_grad():
+        ref = orc.render_chunked(rays, osc, P, nc, nf, chunk=512)
+        got = net.render_rays_test({k: v.to(cuda) for k, v in rays.items()}, chunk=512)
+        wrong = net.render_rays_test({k: v.to(cuda) for k, v in rays.items()}, chunk=0)
+    net.check()
+    for k in ("rgb", "fg_rgb", "bg_rgb", "depth"):
+        rk = "comp_rgb" if k == "rgb" else k
+        diff = (got[k].cpu() - ref[rk]).abs()
+        assert float(diff.max()) < 1e-3 and float((diff > 2e-4).float().mean()) < 0.01, (k, float(diff.max()))
+    assert orc.psnr(got["rgb"].cpu(), ref["comp_rgb"]) > 60
+    # sanity: ignoring the chunk size gives a measurably different image (the quirk is real and reproduced)
+    assert float((wrong["rgb"].cpu() - ref["comp_rgb"]).abs().max()) > 1e-3
