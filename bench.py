@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the NeO-360 ray-marching hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): NeO-360 tri-planar render, 3 source views, 640x480 target frame,
+128 coarse + 64 fine samples per ray and branch (129 + 193 points, fg and bg => 644 field evaluations per ray,
+each over 3 views), chunk=1024 semantics (quirk Q1), synthetic NERDS360-shaped scene (neo360_b200/synth.py).
+One "step" = one full frame (307 200 rays) through the hot path.  N GPUs: every rank renders its own frame of the
+turntable (weak scaling, no data-path collective), value = all rays of all ranks / max-over-ranks device time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [...]                         the reference algorithm (CPU oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  See the prompt contract for the keys; `roofline` is for the dominant kernel (the
+field kernel: lookups + MLP), `cpu_baseline` is the oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_W, IMG_H = 640, 480
+N_COARSE, N_FINE, NV, CHUNK = 128, 64, 3, 1024
+# reference-formulation MACs per (point, all 3 views): SURVEY.md section 8(a) a10
+FLOP_PER_POINT = {0: 2 * 770688, 1: 2 * 786816}          # fg, bg
+POINTS_PER_RAY = (N_COARSE + 1) + (N_COARSE + 1 + N_FINE)  # per branch
+FLOP_PER_RAY = POINTS_PER_RAY * (FLOP_PER_POINT[0] + FLOP_PER_POINT[1])   # 1.003 GFLOP
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NEO360_PRECISION", "tc"), choices=["tc", "fp32"])
+    ap.add_argument("--rays", type=int, default=IMG_W * IMG_H, help="debug only: fewer rays per step (not a valid headline)")
+    ap.add_argument("--cpu-sample-rays", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops_sustained"], "burst": d["bf16_tflops"], "hbm_gbs": d["hbm_gbs"], "src": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"bf16_tflops": 1400.0, "burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "sw_power_cap": 0x4, "hw_power_brake_slowdown": 0x80}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that rather than inventing clocks
+            self.reasons.add("nvml_unavailable:" + type(e).__name__)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_scene_cpu():
+    from neo360_b200 import synth
+    sc = synth.make_scene((IMG_W, IMG_H), NV, (120, 160), seed=0)
+    P = synth.make_mlp_params(0)
+    return sc, P
+
+
+def frame_rays_cpu(view):
+    """Host-side ray generation for frame `view` of the 100-view turntable (datasets/ray_utils.py:84-176 semantics)."""
+    import torch
+    from neo360_b200 import synth
+    pose = synth.target_pose(view, 100)
+    j, i = torch.meshgrid(torch.arange(IMG_H, dtype=torch.float32), torch.arange(IMG_W, dtype=torch.float32), indexing="ij")
+    f = 0.8 * IMG_W
+    dirs = torch.stack([(i - IMG_W / 2) / f, -(j - IMG_H / 2) / f, -torch.ones_like(i)], -1)
+    d = dirs @ pose[:3, :3].T
+    d = (d / d.norm(dim=-1, keepdim=True)).reshape(-1, 3)
+    o = pose[:3, 3].expand(d.shape).contiguous()
+    return o, d
+
+
+def cpu_reference_rate(sc, P, n_rays, steps=1, warmup=0, threads=None):
+    """The reference's algorithm (oracle port, F.grid_sample lookups, eager torch CPU) on `n_rays` rays of frame 0,
+    chunk = 1024 as the reference's render loop; encoder hoisted.  Returns (rays/s, seconds per step list)."""
+    import torch
+    from oracle import neo360_oracle as orc
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
+    o, d = frame_rays_cpu(0)
+    start = (IMG_H // 2) * IMG_W
+    rays = {"rays_o": o[start:start + n_rays].contiguous(), "rays_d": d[start:start + n_rays].contiguous(),
+            "viewdirs": d[start:start + n_rays].contiguous()}
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.render_chunked(rays, osc, P, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    return n_rays * len(times) / sum(times), times, threads
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "neo360 tri-planar render, 3 src views, 640x480, 128+64 samples (BASELINE configs[1])"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sc, P = build_scene_cpu()
+        rate, times, threads = cpu_reference_rate(sc, P, args.cpu_sample_rays, steps=args.steps, warmup=args.warmup)
+        ms = 1e3 * sum(times) / len(times)
+        line = {"impl": "reference", "metric": "rays/sec at 640x480, 192 samples/ray", "value": rate, "unit": "rays/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "rays_per_step": args.cpu_sample_rays, "chunk": CHUNK,
+                           "note": "reference algorithm = CPU oracle port (eager torch, F.grid_sample), encoder hoisted; each step a bounded sample of the frame"},
+                "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                                 "sample": f"{args.cpu_sample_rays} rays (one reference chunk) of frame 0 per step"},
+                "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import ctypes as C
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from neo360_b200 import NeRF_TP, _lib as L, build
+    build.build()
+    lib = L.load()
+
+    sc, P = build_scene_cpu()
+    net = NeRF_TP(num_coarse_samples=N_COARSE, num_fine_samples=N_FINE, num_src_views=NV, precision=args.precision).eval()
+    net.load_state_dict(P)
+    net = net.to(dev)
+    net.set_scene(*[sc[k].to(dev) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")],
+                  sc["img_wh"])
+    n = args.rays
+    total_steps = args.warmup + args.steps
+    # per-step inputs: a different turntable frame per (step, rank); pinned host copies for the e2e leg
+    host = []
+    for s in range(min(total_steps, 4)):
+        o, d = frame_rays_cpu((s * world + rank) % 100)
+        host.append((o[:n].contiguous().pin_memory(), d[:n].contiguous().pin_memory()))
+    devrays = [{"rays_o": o.to(dev), "rays_d": d.to(dev), "viewdirs": d.to(dev)} for (o, d) in host]
+    out_host = torch.empty(n, 4).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(s):
+        return net.render_rays_test(devrays[s % len(devrays)], chunk=CHUNK)
+
+    def step_e2e(s):
+        o, d = host[s % len(host)]
+        do, dd = o.to(dev, non_blocking=True), d.to(dev, non_blocking=True)
+        r = net.render_rays_test({"rays_o": do, "rays_d": dd, "viewdirs": dd}, chunk=CHUNK)
+        out_host[:, :3].copy_(r["rgb"], non_blocking=True)
+        out_host[:, 3].copy_(r["depth"], non_blocking=True)
+        return r
+
+    def timed(fn, sampler=None):
+        with torch.no_grad():
+            for s in range(args.warmup):
+                fn(s)
+            barrier()
+            if sampler:
+                sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(args.steps):
+                fn(args.warmup + s)
+            e1.record()
+            barrier()
+            if sampler:
+                sampler.stop_flag = True
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.neo_profile(0)
+    ms_res = timed(step_resident, sampler)
+    launches = C.c_ulonglong()
+    lib.neo_profile_read(None, None, C.byref(launches), None)
+    net.check()
+    ms_e2e = timed(step_e2e)
+    # roofline of the dominant kernel: CUDA events around every field launch, on the launching stream
+    lib.neo_profile(1)
+    with torch.no_grad():
+        for s in range(args.steps):
+            step_resident(args.warmup + s)
+    fms, nf, _l, pts = C.c_float(), C.c_int(), C.c_ulonglong(), C.c_double()
+    lib.neo_profile_read(C.byref(fms), C.byref(nf), C.byref(_l), C.byref(pts))
+    lib.neo_profile(0)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    rays_total = n * args.steps * world
+    value = rays_total / (ms_res * 1e-3)
+    e2e = rays_total / (ms_e2e * 1e-3)
+    # each field launch handles one branch; fg and bg launches alternate, so the mean flop/point is the fg/bg average
+    flops_alg = pts.value * 0.5 * (FLOP_PER_POINT[0] + FLOP_PER_POINT[1])
+    ach = flops_alg / (fms.value * 1e-3) / 1e12
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        traffic = json.load(open(tj)).get(args.precision)
+    line = {
+        "metric": "rays/sec at 640x480, 192 samples/ray", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
+        "data": "synthetic",
+        "config": {"workload": workload, "rays_per_step_per_gpu": n, "chunk": CHUNK, "precision": args.precision,
+                   "parallelism": f"ray-sharded x{world} (one frame per rank, no collective)",
+                   "l2": "inputs larger than L2 (feature maps + per-sample workspace >> 126 MB)",
+                   "valid_headline": n == IMG_W * IMG_H},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": ach / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["src"],
+                     "kernel": "field kernel (lookups + MLP), %d launches, %.3f ms mean" % (nf.value, fms.value / max(nf.value, 1)),
+                     "flops": "reference-formulation algorithmic FLOPs (2*MAC of NeRFPPMLP incl. latent columns), SURVEY.md 8(d)",
+                     "share_of_step": (fms.value / args.steps) / (ms_res / args.steps)},
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * n * 3 * 4, "d2h_bytes_per_step": n * 4 * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches.value),
+        "clocks": sampler.result(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        rate, times, threads = cpu_reference_rate(sc, P, args.cpu_sample_rays, steps=1, warmup=0)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_sample_rays} rays (one reference chunk of frame 0), {times[0]:.1f} s"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

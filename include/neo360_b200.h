@@ -177,6 +177,11 @@ int neo_index_local(const NeoScene* scene, const float* pts, int M, float* out, 
 int neo_field_eval(const NeoScene* scene, const NeoRays* rays, const float* far, const float* t_vals, int N,
                    int mlp_index, int precision, float* rgb, float* sigma, void* stream);
 
+/* bench support: CUDA events around every field-kernel launch on the launching stream + launch accounting.
+ * neo_profile(1) resets and enables, neo_profile(0) resets and disables; neo_profile_read synchronises. */
+int neo_profile(int enable);
+int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches, double* points);
+
 const char* neo_last_error(void);
 /* "neo360_b200 <version> sm_100a" */
 const char* neo_version(void);

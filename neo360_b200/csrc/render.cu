@@ -50,10 +50,36 @@ int check_cfg(const NeoCfg* cfg) {
     return NEO_OK;
 }
 
+// ---- optional profiling: CUDA events around every field-kernel launch, on the launching stream ----
+struct Prof {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+    size_t used = 0;
+    unsigned long long launches = 0;     // kernels launched by this library since the last reset
+    double field_points = 0;             // (ray, sample) points pushed through field kernels
+} g_prof;
+
 int field(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mi, int prec, float* rgb,
           float* sigma, cudaStream_t s) {
-    if (prec == NEO_PREC_FP32) return launch_field_fp32(sc, rays, far, t, N, mi, rgb, sigma, s);
-    return launch_field_tc(sc, rays, far, t, N, mi, rgb, sigma, s);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof.on) {
+        if (g_prof.used == g_prof.pool.size()) {
+            cudaEvent_t a, b;
+            NEO_CUDA(cudaEventCreate(&a));
+            NEO_CUDA(cudaEventCreate(&b));
+            g_prof.pool.emplace_back(a, b);
+        }
+        e0 = g_prof.pool[g_prof.used].first;
+        e1 = g_prof.pool[g_prof.used].second;
+        g_prof.used++;
+        NEO_CUDA(cudaEventRecord(e0, s));
+    }
+    int rc = (prec == NEO_PREC_FP32) ? launch_field_fp32(sc, rays, far, t, N, mi, rgb, sigma, s)
+                                     : launch_field_tc(sc, rays, far, t, N, mi, rgb, sigma, s);
+    if (g_prof.on && e1) NEO_CUDA(cudaEventRecord(e1, s));
+    g_prof.launches += 1;
+    g_prof.field_points += (double)rays->n_rays * N;
+    return rc;
 }
 
 int copy_out(float* dst, const float* src, size_t n, cudaStream_t s) {
@@ -86,6 +112,7 @@ extern "C" int neo_render_fwd(const NeoScene* sc, const NeoRays* rays, const Neo
     if (!workspace || workspace_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes); return NEO_ERR_WORKSPACE; }
 
     if ((rc = launch_far(rays->rays_o, rays->rays_d, n, w.far, sc->err_flag, s))) return rc;
+    g_prof.launches += 1 + 2 * (2 + 2 + 1);      // far + per level: 2 sampling, 2 composite, 1 combine (field counted in field())
     const int white = cfg->out_depth ? 0 : cfg->white_bkgd;       // model.py:501,519 vs 551,560
     for (int lvl = 0; lvl < 2; ++lvl) {
         const int N = lvl ? N1 : N0;
@@ -173,4 +200,29 @@ extern "C" int neo_field_eval(const NeoScene* sc, const NeoRays* rays, const flo
                               int precision, float* rgb, float* sigma, void* stream) {
     if (!sc || !rays || mlp_index < 0 || mlp_index > 3 || N < 1) { set_error("neo_field_eval: bad arguments"); return NEO_ERR_INVALID; }
     return field(sc, rays, far, t, N, mlp_index, precision, rgb, sigma, (cudaStream_t)stream);
+}
+
+// ---- profiling / accounting (bench.py) ----
+extern "C" int neo_profile(int enable) {
+    g_prof.on = enable != 0;
+    g_prof.used = 0;
+    g_prof.launches = 0;
+    g_prof.field_points = 0;
+    return NEO_OK;
+}
+// Synchronises the device.  field_ms = summed event time of the field-kernel launches since neo_profile(1);
+// n_field = their count; launches = all kernels this library launched; points = (ray,sample) points evaluated.
+extern "C" int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches, double* points) {
+    NEO_CUDA(cudaDeviceSynchronize());
+    float total = 0.f;
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        float ms = 0.f;
+        NEO_CUDA(cudaEventElapsedTime(&ms, g_prof.pool[i].first, g_prof.pool[i].second));
+        total += ms;
+    }
+    if (field_ms) *field_ms = total;
+    if (n_field) *n_field = (int)g_prof.used;
+    if (launches) *launches = g_prof.launches;
+    if (points) *points = g_prof.field_points;
+    return NEO_OK;
 }
