@@ -182,6 +182,11 @@ int neo_field_eval(const NeoScene* scene, const NeoRays* rays, const float* far,
 int neo_profile(int enable);
 int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches, double* points);
 
+/* Self-test of the tcgen05 building blocks of the NEO_PREC_TC path (TMEM-resident A operand, 128B-swizzled K-major
+ * operand tiles, TMEM loads): X (128,128), W (128,128), Wn (80,128) fp32 device -> out1 (128,128) = W X^T,
+ * out2 (128,80) = X Wn^T, computed with fp16 operands / fp32 accumulation. */
+int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, void* stream);
+
 const char* neo_last_error(void);
 /* "neo360_b200 <version> sm_100a" */
 const char* neo_version(void);

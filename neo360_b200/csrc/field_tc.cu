@@ -1,7 +1,889 @@
-// tcgen05 tensor-core path (placeholder until the kernel lands)
+// NEO_PREC_TC: the radiance field of NeO-360 on tcgen05 tensor cores (sm_100a), weight-stationary in TMEM.
+//
+// Formulation (exact re-association of models/neo360/model.py:110-158, see DESIGN.md "TC path"):
+//   * bilinear lookups are linear, so the latent columns of layers 0 and 3 are applied to the feature maps once per
+//     scene:  P0 = W0[:, enc:] . F,  P3 = W3[:, 128+enc:] . F  (F = pixel-aligned latent or a tri-plane).  Per sample
+//     the kernel gathers 4 taps of [P0|P3] (256 fp16 channels) from 4 maps instead of 4 taps of 512+3*128 raw channels.
+//   * bottleneck_layer -> views_linear.0 has no nonlinearity in between and the view mean is linear, so
+//       q = (Wv0[:, :128] Wb / NV) . sum_v h3_v + Wv0[:, 128:] . mean_v(dir_enc_v) + (Wv0[:, :128] bb + bv0)
+//       sigma_raw = (w_sigma / NV) . sum_v h3_v + b_sigma
+//     i.e. the cross-view means become accumulation over the views in one TMEM accumulator.
+//   * trunk layers run transposed, D^T[neuron][point] = W[neuron][k] . X[point][k]:  the weights are the A operand and
+//     live in TMEM for the whole kernel (tcgen05.mma with A from TMEM), the activations X (fp16, K-major, 128B swizzle)
+//     are the B operand in shared memory; the epilogue thread owns a neuron, so its bias is a register.
+//
+// One CTA per SM, persistent over tiles of 128 points (32 rays x 4 consecutive samples); per tile the NV source views
+// are processed in turn.  Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issue, 5-15 producers (geometry,
+// positional encoding, tap tables, tap gathers).  Hand-offs are mbarriers; tcgen05.commit signals MMA completion.
 #include "common.cuh"
+#include <cuda_fp16.h>
+
 namespace neo {
-int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) { set_error("NEO_PREC_TC not built yet"); return NEO_ERR_UNSUPPORTED; }
-void tc_scene_free(NeoScene* sc) {}
-int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mlp_index, float* rgb, float* sigma, cudaStream_t s) { set_error("NEO_PREC_TC not built yet"); return NEO_ERR_UNSUPPORTED; }
+namespace tc {
+
+constexpr int kThreads = 512;
+constexpr int kProducerWarp0 = 5;
+constexpr int kProducerWarps = 11;
+constexpr int kTileRays = 32;
+constexpr int kTileSamples = 4;
+constexpr int kTilePts = 128;
+
+// ---- shared memory map (bytes; UMMA tiles 1024-aligned) ----
+constexpr uint32_t SM_ENC = 0;            // 128 x KE fp16, SW128 K-major, up to 2 slabs of 16 KB
+constexpr uint32_t SM_H = 32768;          // 128 x 128 fp16, 2 slabs
+constexpr uint32_t SM_DIR = 65536;        // 128 x 64 fp16 (32 used), 1 slab
+constexpr uint32_t SM_WHEAD = 81920;      // head weights, B operands
+constexpr uint32_t WH_H = 0, WH_DIR = 20480, WH_V1 = 30720, WH_RGB = 38912, WH_BYTES = 40960;
+constexpr uint32_t SM_G0 = 122880;        // 128 x 128 fp16 row-major
+constexpr uint32_t SM_G3 = 155648;
+constexpr uint32_t SM_ROWTAB = 188416;    // 128 rows x 128 B
+constexpr uint32_t SM_BIAS = 204800;      // fp32: b0..b3 (512) | bq (64) | bv1 (64) | brgb (4) | bsig (1)
+constexpr uint32_t SM_BAR = 207872;
+constexpr uint32_t SM_TOTAL = 208128;
+constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
+
+// TMEM column map (512 columns allocated)
+constexpr uint32_t TM_D = 0;        // trunk accumulator (128) ; also Dq (64) / Drgb (16)
+constexpr uint32_t TM_DH = 128;     // head accumulator (80)
+constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
+
+enum Bar { ENC_READY = 0, ENC_FREE, G0_READY, G0_FREE, G3_READY, G3_FREE, ACC_READY, H_READY, HEAD_READY, DIR_FREE, NUM_BARS };
+
+struct MlpTc {
+    int in_ch, enc_dim, KE;          // 3|4, 63|84, 64|96
+    const uint32_t* wimg;            // [KW/2][128] TMEM image words
+    const float* bias;               // BIAS_FLOATS
+    const uint4* headimg;            // WH_BYTES pre-swizzled
+    const __half* plocal;            // [nv][lat_hw][256]
+    const __half* pplane[3];         // [nv][plane_hw][256]
+};
+
+struct State {
+    MlpTc mlp[4];
+};
+
+struct Params {
+    const float *rays_o, *rays_d, *viewdirs, *far, *tvals;
+    const int* ray_order;
+    int n_rays, N, chunk, nv, n_tiles, sg;
+    float far_unc;
+    SceneDev sc;
+    MlpTc mlp;
+    float* rgb_out;
+    float* sigma_out;
+    int* err;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {      // ~2 s
+            if (err) atomicExch(err, 1000 + tag);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand descriptor: rows of 128 B (64 fp16), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);     // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset (ignored for swizzled K-major; CUTLASS writes 1)
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B, fp32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T     (A: M x 16 from TMEM, B: N x 16 K-major from smem)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned short lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of element (row, k) inside a SW128 K-major tile whose slabs hold `rows` rows
+__host__ __device__ inline uint32_t sw128_off(int row, int k, int rows) {
+    int slab = k >> 6, kk = k & 63;
+    return (uint32_t)slab * (uint32_t)rows * 128u + (uint32_t)row * 128u + (uint32_t)((((kk >> 3) ^ (row & 7)) << 4) + (kk & 7) * 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-scene preparation kernels
+// ------------------------------------------------------------------------------------------------
+// P[(v*HW + p)*256 + half*128 + n] = sum_c W[n*ldw + col0 + c] * in[(v*C + c)*HW + p]        (fp32 math, fp16 store)
+__global__ void __launch_bounds__(256) preproject_kernel(const float* __restrict__ in, int C, int HW,
+                                                         const float* __restrict__ W, int ldw, int col0, int half_sel,
+                                                         __half* __restrict__ out) {
+    __shared__ float As[16][64 + 4];   // [k][pixel]
+    __shared__ float Bs[16][64 + 4];   // [k][n]
+    const int v = blockIdx.z, p0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;      // tx -> n, ty -> pixel
+    float acc[4][4] = {};
+    const float* inv = in + (size_t)v * C * HW;
+    for (int k0 = 0; k0 < C; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            int kk = e / 64, pp = e % 64;
+            int p = p0 + pp;
+            As[kk][pp] = (p < HW) ? inv[(size_t)(k0 + kk) * HW + p] : 0.f;
+        }
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            int nn = e / 16, kk = e % 16;
+            Bs[kk][nn] = W[(size_t)(n0 + nn) * ldw + col0 + k0 + kk];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+        int p = p0 + ty * 4 + i;
+        if (p >= HW) continue;
+        __half* o = out + ((size_t)v * HW + p) * 256 + half_sel * 128 + n0 + tx * 4;
+        o[0] = __float2half_rn(acc[i][0]); o[1] = __float2half_rn(acc[i][1]);
+        o[2] = __float2half_rn(acc[i][2]); o[3] = __float2half_rn(acc[i][3]);
+    }
+}
+
+// TMEM weight image: word j of neuron n = fp16(Wcat[n][2j]) | fp16(Wcat[n][2j+1]) << 16,
+// Wcat = [W0enc (KE) | W1 (128) | W2 (128) | W3h (128) | W3enc (KE)]
+__global__ void wimg_kernel(NeoMLPParams p, int enc_dim, int KE, uint32_t* __restrict__ out) {
+    const int KW = 2 * KE + 384;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (KW / 2) * 128) return;
+    int j = idx / 128, n = idx % 128;
+    const int in_dim = enc_dim + kLocalCh + kWorldCh;
+    float v[2];
+    for (int h = 0; h < 2; ++h) {
+        int k = 2 * j + h;
+        float x;
+        if (k < KE) x = (k < enc_dim) ? p.w0[(size_t)n * in_dim + k] : 0.f;
+        else if (k < KE + 128) x = p.w1[n * 128 + (k - KE)];
+        else if (k < KE + 256) x = p.w2[n * 128 + (k - KE - 128)];
+        else if (k < KE + 384) x = p.w3[(size_t)n * (128 + in_dim) + (k - KE - 256)];
+        else { int kk = k - KE - 384; x = (kk < enc_dim) ? p.w3[(size_t)n * (128 + in_dim) + 128 + kk] : 0.f; }
+        v[h] = x;
+    }
+    out[idx] = pack_h2(v[0], v[1]);
+}
+
+// head weights (pre-swizzled smem image) + folded biases
+__global__ void head_kernel(NeoMLPParams p, int nv, unsigned char* __restrict__ img, float* __restrict__ bias) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    __half* im = reinterpret_cast<__half*>(img);
+    const float inv = 1.0f / (float)nv;
+    if (idx < 80 * 128) {                 // Whead_h  (rows: 64 q rows, 1 sigma row, 15 zero rows)
+        int r = idx / 128, k = idx % 128;
+        float x = 0.f;
+        if (r < 64) { for (int j = 0; j < 128; ++j) x = fmaf(p.wv0[r * 155 + j], p.wb[j * 128 + k], x); x *= inv; }
+        else if (r == 64) x = p.wsig[k] * inv;
+        im[(WH_H + sw128_off(r, k, 80)) / 2] = __float2half_rn(x);
+    } else if (idx < 80 * 128 + 80 * 64) { // Whead_dir
+        int e = idx - 80 * 128, r = e / 64, k = e % 64;
+        float x = (r < 64 && k < kDirEnc) ? p.wv0[r * 155 + 128 + k] : 0.f;
+        im[(WH_DIR + sw128_off(r, k, 80)) / 2] = __float2half_rn(x);
+    } else if (idx < 80 * 128 + 80 * 64 + 64 * 64) {
+        int e = idx - 80 * 128 - 80 * 64, r = e / 64, k = e % 64;
+        im[(WH_V1 + sw128_off(r, k, 64)) / 2] = __float2half_rn(p.wv1[r * 64 + k]);
+    } else if (idx < 80 * 128 + 80 * 64 + 64 * 64 + 16 * 64) {
+        int e = idx - 80 * 128 - 80 * 64 - 64 * 64, r = e / 64, k = e % 64;
+        im[(WH_RGB + sw128_off(r, k, 16)) / 2] = __float2half_rn(r < 3 ? p.wrgb[r * 64 + k] : 0.f);
+    }
+    if (idx < BIAS_FLOATS) {
+        float x = 0.f;
+        if (idx < 128) x = p.b0[idx];
+        else if (idx < 256) x = p.b1[idx - 128];
+        else if (idx < 384) x = p.b2[idx - 256];
+        else if (idx < 512) x = p.b3[idx - 384];
+        else if (idx < 576) { int r = idx - 512; x = p.bv0[r]; for (int j = 0; j < 128; ++j) x = fmaf(p.wv0[r * 155 + j], p.bb[j], x); }
+        else if (idx < 640) x = p.bv1[idx - 576];
+        else if (idx < 643) x = p.brgb[idx - 640];
+        else if (idx == 644) x = p.bsig[0];
+        bias[idx] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the field kernel
+// ------------------------------------------------------------------------------------------------
+struct TapRow {        // 128 bytes: 4 maps x (4 texel indices, 4 weights as half2(w,w))
+    int idx[4][4];
+    uint32_t w2[4][4];
+};
+
+template <int ICH>
+__device__ __forceinline__ void write_enc_row(uint32_t enc_base, int n, const float* x) {
+    constexpr int ENC = ICH * 21, KE = (ICH == 3) ? 64 : 96;
+#pragma unroll
+    for (int c = 0; c < KE / 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = c * 8 + i;
+            if (e >= ENC) v[i] = 0.f;
+            else if (e < ICH) v[i] = x[e];
+            else {
+                constexpr int HALF = ICH * kPosDeg;
+                const int q0 = e - ICH;
+                const bool shifted = q0 >= HALF;
+                const int q = shifted ? q0 - HALF : q0;
+                const int k = q / ICH, cc = q % ICH;
+                float xb = x[cc] * (float)(1 << k);
+                v[i] = __sinf(shifted ? xb + 1.57079637f : xb);     // helper.py:124
+            }
+        }
+        uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        const int slab = c >> 3, cc8 = c & 7;
+        sts128(enc_base + slab * 16384 + n * 128 + ((cc8 ^ (n & 7)) << 4), pk);
+    }
+}
+
+__device__ __forceinline__ void taps_to_row(const Taps& t, int (&idx)[4], uint32_t (&w2)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { idx[i] = t.idx[i]; w2[i] = pack_h2(t.w[i], t.w[i]); }
+}
+
+template <int ICH>
+__global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    constexpr int KE = (ICH == 3) ? 64 : 96;
+    constexpr bool IS_BG = (ICH == 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sbase + SM_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + SM_BAR + 8 * NUM_BARS);
+
+    // ---- one-time setup ----
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(ENC_READY), kProducerWarps * 32);
+        mbar_init(BAR(ENC_FREE), 1);
+        mbar_init(BAR(G0_READY), kProducerWarps * 32);
+        mbar_init(BAR(G0_FREE), 128);
+        mbar_init(BAR(G3_READY), kProducerWarps * 32);
+        mbar_init(BAR(G3_FREE), 128);
+        mbar_init(BAR(ACC_READY), 1);
+        mbar_init(BAR(H_READY), 128);
+        mbar_init(BAR(HEAD_READY), 1);
+        mbar_init(BAR(DIR_FREE), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(sbase + SM_BAR + 8 * NUM_BARS, 512);
+    {   // head weights + biases -> smem
+        const uint4* src = P.mlp.headimg;
+        for (int i = threadIdx.x; i < (int)(WH_BYTES / 16); i += kThreads) sts128(sbase + SM_WHEAD + 16 * i, __ldg(src + i));
+        float* bsm = reinterpret_cast<float*>(sgen + SM_BIAS);
+        for (int i = threadIdx.x; i < BIAS_FLOATS; i += kThreads) bsm[i] = __ldg(P.mlp.bias + i);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp < 4) {   // trunk weights -> TMEM (thread = neuron = TMEM lane)
+        constexpr int NW = (2 * KE + 384) / 2;
+        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + TM_W;
+        const int n = warp * 32 + lane;
+        for (int j0 = 0; j0 < NW; j0 += 16) {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __ldg(P.mlp.wimg + (size_t)(j0 + i) * 128 + n);
+            tmem_st16(tw + j0, r);
+        }
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int nv = P.nv, N = P.N;
+    const long long total_pts = (long long)P.n_rays * N;
+    (void)total_pts;
+
+    if (warp >= kProducerWarp0) {
+        // =====================================================================================
+        // PRODUCERS: geometry + positional encoding + tap tables, then the two gather passes
+        // =====================================================================================
+        const int pw = warp - kProducerWarp0, ptid = threadIdx.x - kProducerWarp0 * 32;
+        uint32_t ph_enc_free = 1, ph_g0_free = 1, ph_g3_free = 1, ph_dir_free = 1;
+        const uint32_t rowtab = sbase + SM_ROWTAB;
+        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            const int g = t / P.sg, q = t % P.sg;
+            for (int v = 0; v < nv; ++v) {
+                // all producer warps must be done reading ROWTAB of the previous job
+                asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
+                mbar_wait(BAR(ENC_FREE), ph_enc_free, P.err, 1); ph_enc_free ^= 1;
+                if (v == 0) { mbar_wait(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
+                if (ptid < kTilePts) {
+                    const int n = ptid, rl = n & 31, sl = n >> 5;
+                    const int slot = min(g * kTileRays + rl, P.n_rays - 1);
+                    const int rid = P.ray_order ? P.ray_order[slot] : slot;
+                    const int s = min(q * kTileSamples + sl, N - 1);
+                    RayGeom rg;
+                    ray_geom(P.rays_o + 3 * rid, P.rays_d + 3 * rid, rg, IS_BG);
+                    rg.far = P.far[rid];
+                    const float tv = P.tvals[(long long)rid * N + s];
+                    float xe[3], xl[3];
+                    if (IS_BG) bg_point(rg, tv, P.far_unc, xe, xl);
+                    else { fg_point(rg, tv, xe); xl[0] = xe[0]; xl[1] = xe[1]; xl[2] = xe[2]; }
+                    const ViewXform vx = P.sc.views[v];
+                    float ce[4], cl[3];
+                    to_camera(vx, xe, ce);
+                    to_camera(vx, xl, cl);
+                    ce[3] = tv;
+                    write_enc_row<ICH>(sbase + SM_ENC, n, ce);
+                    TapRow tr;
+                    Taps tp;
+                    float gx, gy;
+                    local_grid_coords(P.sc, cl, gx, gy);
+                    bilinear_taps(gx, gy, P.sc.lat_w, P.sc.lat_h, tp); taps_to_row(tp, tr.idx[0], tr.w2[0]);
+                    bilinear_taps(cl[0], cl[2], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[1], tr.w2[1]);
+                    bilinear_taps(cl[0], cl[1], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[2], tr.w2[2]);
+                    bilinear_taps(cl[1], cl[2], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[3], tr.w2[3]);
+                    const uint4* trv = reinterpret_cast<const uint4*>(&tr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sts128(rowtab + n * 128 + 16 * i, trv[i]);
+                    if (v == 0) {
+                        // mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360)
+                        const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
+                        const int c0 = (rid / ch) * ch;
+                        const int Bc = min(ch, P.n_rays - c0);
+                        const long long jl = (long long)(rid - c0) * N + s;
+                        const int src = c0 + (int)(jl % Bc);
+                        const float* wd = P.viewdirs + 3 * src;
+                        float acc[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                        for (int vv = 0; vv < nv; ++vv) {
+                            float dc[3];
+                            rotate_to_camera(P.sc.views[vv], wd, dc);
+#pragma unroll
+                            for (int i = 0; i < kDirEnc; ++i) {
+                                float val;
+                                if (i < 3) val = dc[i];
+                                else {
+                                    const int q0 = i - 3;
+                                    const bool shifted = q0 >= 12;
+                                    const int qq = shifted ? q0 - 12 : q0;
+                                    const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
+                                    val = __sinf(shifted ? xb + 1.57079637f : xb);
+                                }
+                                acc[i] += val;
+                            }
+                        }
+                        const float inv = 1.0f / (float)nv;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 pk = make_uint4(pack_h2(acc[8 * c] * inv, acc[8 * c + 1] * inv), pack_h2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
+                                                  pack_h2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv), pack_h2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
+                            sts128(sbase + SM_DIR + n * 128 + ((c ^ (n & 7)) << 4), pk);
+                        }
+                    }
+                }
+                fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
+                mbar_arrive(BAR(ENC_READY));
+                asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB complete
+                // ---- gather passes: G0 (layer-0 features) then G3 (layer-3 features) ----
+                const size_t lat_hw = (size_t)P.sc.lat_h * P.sc.lat_w, pl_hw = (size_t)P.sc.plane_h * P.sc.plane_w;
+                const __half* mapbase[4] = {P.mlp.plocal + (size_t)v * lat_hw * 256, P.mlp.pplane[0] + (size_t)v * pl_hw * 256,
+                                            P.mlp.pplane[1] + (size_t)v * pl_hw * 256, P.mlp.pplane[2] + (size_t)v * pl_hw * 256};
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (pass == 0) { mbar_wait(BAR(G0_FREE), ph_g0_free, P.err, 3); ph_g0_free ^= 1; }
+                    else { mbar_wait(BAR(G3_FREE), ph_g3_free, P.err, 4); ph_g3_free ^= 1; }
+                    const uint32_t gdst = sbase + (pass == 0 ? SM_G0 : SM_G3);
+#pragma unroll 1
+                    for (int r = pw; r < kTilePts; r += kProducerWarps) {
+                        uint4 tb[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) tb[i] = lds128(rowtab + r * 128 + 16 * i);
+                        const int* ti = reinterpret_cast<const int*>(&tb[0]);        // idx[4][4]
+                        const uint32_t* tw = reinterpret_cast<const uint32_t*>(&tb[4]);   // w2[4][4]
+                        uint2 val[16];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                val[m * 4 + k] = __ldg(reinterpret_cast<const uint2*>(mapbase[m] + (size_t)ti[m * 4 + k] * 256 + pass * 128) + lane);
+                        float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __half2 w = *reinterpret_cast<const __half2*>(&tw[m * 4 + k]);
+                                a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&val[m * 4 + k].x), a0);
+                                a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&val[m * 4 + k].y), a1);
+                            }
+                            const float2 x0 = __half22float2(a0), x1 = __half22float2(a1);
+                            f[0] += x0.x; f[1] += x0.y; f[2] += x1.x; f[3] += x1.y;
+                        }
+                        sts64(gdst + r * 256 + lane * 8, make_uint2(pack_h2(f[0], f[1]), pack_h2(f[2], f[3])));
+                    }
+                    mbar_arrive(BAR(pass == 0 ? G0_READY : G3_READY));
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =====================================================================================
+        // MMA ISSUE (one thread)
+        // =====================================================================================
+        if (lane == 0) {
+            uint32_t ph_enc = 0, ph_h = 0;
+            const uint32_t id_trunk = idesc_f16(128, 128), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
+            const uint32_t dD = tmem + TM_D, dH = tmem + TM_DH;
+            const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
+            const uint32_t sENC = sbase + SM_ENC, sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
+            auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
+            for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+                for (int v = 0; v < nv; ++v) {
+                    mbar_wait(BAR(ENC_READY), ph_enc, P.err, 10); ph_enc ^= 1;
+                    tc_fence_after();
+                    // L0: D = W0enc . ENC^T
+#pragma unroll
+                    for (int ks = 0; ks < KE / 16; ++ks)
+                        mma_ts(dD, aW0 + ks * 8, desc_sw128(kaddr(sENC, ks, 16384)), id_trunk, ks > 0);
+                    tc_commit(BAR(ACC_READY));
+                    // L1, L2
+                    for (int l = 1; l <= 2; ++l) {
+                        mbar_wait(BAR(H_READY), ph_h, P.err, 11); ph_h ^= 1;
+                        tc_fence_after();
+                        const uint32_t aW = (l == 1) ? aW1 : aW2;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW + ks * 8, desc_sw128(kaddr(sH, ks, 16384)), id_trunk, ks > 0);
+                        tc_commit(BAR(ACC_READY));
+                    }
+                    // L3: D = W3h . H^T + W3enc . ENC^T
+                    mbar_wait(BAR(H_READY), ph_h, P.err, 12); ph_h ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW3h + ks * 8, desc_sw128(kaddr(sH, ks, 16384)), id_trunk, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW3e + ks * 8, desc_sw128(kaddr(sENC, ks, 16384)), id_trunk, 1);
+                    tc_commit(BAR(ACC_READY));
+                    tc_commit(BAR(ENC_FREE));
+                    // head: Dh (+)= H3 . (Whead_h)^T      (points on lanes, accumulates the view mean)
+                    mbar_wait(BAR(H_READY), ph_h, P.err, 13); ph_h ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ss(dH, desc_sw128(kaddr(sH, ks, 16384)), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
+                    if (v == nv - 1) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            mma_ss(dH, desc_sw128(sDIR + ks * 32), desc_sw128(sWH + WH_DIR + ks * 32), id_head, 1);
+                        tc_commit(BAR(HEAD_READY));
+                        tc_commit(BAR(DIR_FREE));
+                    }
+                }
+                // colour head: q -> relu -> 64x64 -> relu -> 64x3
+                mbar_wait(BAR(H_READY), ph_h, P.err, 14); ph_h ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_V1 + ks * 32), id_q, ks > 0);
+                tc_commit(BAR(ACC_READY));
+                mbar_wait(BAR(H_READY), ph_h, P.err, 15); ph_h ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_RGB + ks * 32), id_rgb, ks > 0);
+                tc_commit(BAR(ACC_READY));
+                // accumulator drained by the colour epilogue before the next tile overwrites it
+                mbar_wait(BAR(H_READY), ph_h, P.err, 16); ph_h ^= 1;
+                tc_fence_after();
+            }
+        }
+    } else {
+        // =====================================================================================
+        // EPILOGUE (4 warps).  Trunk: thread = neuron (TMEM lane).  Head: thread = point.
+        // =====================================================================================
+        const int c = warp * 32 + lane;                 // neuron (trunk) / point row (head)
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t ph_acc = 0, ph_g0 = 0, ph_g3 = 0, ph_head = 0;
+        uint32_t hoff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hoff[j] = (uint32_t)(c >> 6) * 16384u + (uint32_t)(((((c & 63) >> 3) ^ j) << 4) + (c & 7) * 2);
+        const uint32_t sH = sbase + SM_H, sBias = sbase + SM_BIAS;
+        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            const int g = t / P.sg, q = t % P.sg;
+            for (int v = 0; v < nv; ++v) {
+#pragma unroll 1
+                for (int l = 0; l < 4; ++l) {
+                    const float bias = lds_f32(sBias + 4 * (l * 128 + c));
+                    mbar_wait(BAR(ACC_READY), ph_acc, P.err, 20 + l); ph_acc ^= 1;
+                    tc_fence_after();
+                    uint32_t gsrc = 0;
+                    if (l == 0) { mbar_wait(BAR(G0_READY), ph_g0, P.err, 24); ph_g0 ^= 1; gsrc = sbase + SM_G0 + c * 2; }
+                    if (l == 3) { mbar_wait(BAR(G3_READY), ph_g3, P.err, 25); ph_g3 ^= 1; gsrc = sbase + SM_G3 + c * 2; }
+#pragma unroll 1
+                    for (int cb = 0; cb < 4; ++cb) {
+                        uint32_t r[32];
+                        tmem_ld32(lane_base + TM_D + cb * 32, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int n = cb * 32 + i;
+                            float x = __uint_as_float(r[i]) + bias;
+                            if (gsrc) x += __half2float(__ushort_as_half(lds16(gsrc + n * 256)));
+                            x = fmaxf(x, 0.f);
+                            sts16(sH + n * 128 + hoff[i & 7], __half_as_ushort(__float2half_rn(x)));
+                        }
+                    }
+                    if (l == 0) mbar_arrive(BAR(G0_FREE));
+                    if (l == 3) mbar_arrive(BAR(G3_FREE));
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(BAR(H_READY));
+                }
+            }
+            // ---- head epilogue: thread = point row c ----
+            const int rl = c & 31, sl = c >> 5;
+            const int slot = g * kTileRays + rl, s = q * kTileSamples + sl;
+            const bool valid = slot < P.n_rays && s < N;
+            const int rid = P.ray_order ? P.ray_order[min(slot, P.n_rays - 1)] : min(slot, P.n_rays - 1);
+            const long long gp = (long long)rid * N + min(s, N - 1);
+            mbar_wait(BAR(HEAD_READY), ph_head, P.err, 26); ph_head ^= 1;
+            tc_fence_after();
+            {
+                uint32_t r[80];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
+                tc_wait_ld();
+                const float raw = __uint_as_float(r[64]) + lds_f32(sBias + 4 * 644);
+                const float xs = raw - 1.0f;                                       // model.py:392-393
+                if (valid) P.sigma_out[gp] = xs > 20.f ? xs : log1pf(expf(xs));
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (512 + ch * 8 + i)), 0.f);
+                    sts128(sH + c * 128 + ((ch ^ (c & 7)) << 4),
+                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                }
+            }
+            tc_fence_before(); fence_proxy_async(); mbar_arrive(BAR(H_READY));
+            mbar_wait(BAR(ACC_READY), ph_acc, P.err, 27); ph_acc ^= 1;
+            tc_fence_after();
+            {
+                uint32_t r[64];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmem_ld16(lane_base + TM_D + 16 * j, r + 16 * j);
+                tc_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (576 + ch * 8 + i)), 0.f);
+                    sts128(sH + c * 128 + ((ch ^ (c & 7)) << 4),
+                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                }
+            }
+            tc_fence_before(); fence_proxy_async(); mbar_arrive(BAR(H_READY));
+            mbar_wait(BAR(ACC_READY), ph_acc, P.err, 28); ph_acc ^= 1;
+            tc_fence_after();
+            {
+                uint32_t r[16];
+                tmem_ld16(lane_base + TM_D, r);
+                tc_wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float a = __uint_as_float(r[k]) + lds_f32(sBias + 4 * (640 + k));
+                        P.rgb_out[gp * 3 + k] = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;   // model.py:395-397
+                    }
+                }
+            }
+            tc_fence_before(); mbar_arrive(BAR(H_READY));
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-test of the tensor-core primitives used above (TS-mode MMA with A in TMEM, SW128 operand tiles, SS-mode MMA)
+//   out1[neuron][point] = sum_k W[neuron][k] * X[point][k]   (K = 128, TS mode)
+//   out2[point][n]      = sum_k X[point][k] * Wn[n][k]       (N = 80,  SS mode)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                          const float* __restrict__ Wn, float* __restrict__ out1,
+                                                          float* __restrict__ out2, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sX = sbase, sWn = sbase + 32768, bar = sbase + 32768 + 20480;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + 32768 + 20480 + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(sbase + 32768 + 20480 + 8, 512);
+    __half* xs = reinterpret_cast<__half*>(sgen);
+    __half* ws = reinterpret_cast<__half*>(sgen + 32768);
+    for (int e = threadIdx.x; e < 128 * 128; e += 128) xs[sw128_off(e / 128, e % 128, 128) / 2] = __float2half_rn(X[e]);
+    for (int e = threadIdx.x; e < 80 * 128; e += 128) ws[sw128_off(e / 128, e % 128, 80) / 2] = __float2half_rn(Wn[e]);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int j0 = 0; j0 < 64; j0 += 16) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = pack_h2(W[c * 128 + 2 * (j0 + i)], W[c * 128 + 2 * (j0 + i) + 1]);
+        tmem_st16(lane_base + 256 + j0, r);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        for (int ks = 0; ks < 8; ++ks)
+            mma_ts(tmem + 0, tmem + 256 + ks * 8, desc_sw128(sX + (ks >> 2) * 16384 + (ks & 3) * 32), idesc_f16(128, 128), ks > 0);
+        for (int ks = 0; ks < 8; ++ks)
+            mma_ss(tmem + 128, desc_sw128(sX + (ks >> 2) * 16384 + (ks & 3) * 32), desc_sw128(sWn + (ks >> 2) * 10240 + (ks & 3) * 32),
+                   idesc_f16(128, 80), ks > 0);
+        tc_commit(bar);
+    }
+    mbar_wait(bar, 0, err, 99);
+    tc_fence_after();
+    for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) out1[c * 128 + cb * 32 + i] = __uint_as_float(r[i]);
+    }
+    for (int j = 0; j < 5; ++j) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + 128 + 16 * j, r);
+        tc_wait_ld();
+        for (int i = 0; i < 16; ++i) out2[c * 80 + 16 * j + i] = __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
+    using namespace tc;
+    const NeoSceneDesc& d = sc->desc;
+    State* st = new State();
+    sc->tc_state = st;
+    const int lat_hw = d.lat_h * d.lat_w, pl_hw = d.plane_h * d.plane_w;
+    const float* planes[3] = {d.planes_xz, d.planes_xy, d.planes_yz};
+    for (int i = 0; i < 4; ++i) {
+        const NeoMLPParams& p = mlps[i];
+        if (p.in_ch != 3 && p.in_ch != 4) { set_error("mlp %d: in_ch must be 3 or 4", i); return NEO_ERR_INVALID; }
+        if ((i & 1) != (p.in_ch == 4)) { set_error("mlps must be ordered fg_coarse, bg_coarse, fg_fine, bg_fine"); return NEO_ERR_INVALID; }
+        MlpTc& m = st->mlp[i];
+        m.in_ch = p.in_ch;
+        m.enc_dim = p.in_ch * 21;
+        m.KE = (p.in_ch == 3) ? 64 : 96;
+        const int in_dim = m.enc_dim + kLocalCh + kWorldCh;
+        void* q = nullptr;
+        int rc;
+        const int nwords = ((2 * m.KE + 384) / 2) * 128;
+        if ((rc = scene_alloc_bytes(sc, &q, (size_t)nwords * 4))) return rc;
+        m.wimg = (const uint32_t*)q;
+        wimg_kernel<<<(nwords + 255) / 256, 256, 0, s>>>(p, m.enc_dim, m.KE, (uint32_t*)q);
+        NEO_LAUNCH_CHECK("wimg_kernel");
+        void* hb = nullptr; void* bb = nullptr;
+        if ((rc = scene_alloc_bytes(sc, &hb, WH_BYTES))) return rc;
+        if ((rc = scene_alloc_bytes(sc, &bb, BIAS_FLOATS * 4))) return rc;
+        NEO_CUDA(cudaMemsetAsync(hb, 0, WH_BYTES, s));
+        head_kernel<<<(80 * 128 + 80 * 64 + 64 * 64 + 16 * 64 + 255) / 256, 256, 0, s>>>(p, d.nv, (unsigned char*)hb, (float*)bb);
+        NEO_LAUNCH_CHECK("head_kernel");
+        m.headimg = (const uint4*)hb;
+        m.bias = (const float*)bb;
+        // pre-projected feature maps [P0 | P3]
+        void* pl = nullptr;
+        if ((rc = scene_alloc_bytes(sc, &pl, (size_t)d.nv * lat_hw * 256 * 2))) return rc;
+        m.plocal = (const __half*)pl;
+        dim3 gl((lat_hw + 63) / 64, 2, d.nv);
+        preproject_kernel<<<gl, 256, 0, s>>>(d.latent, kLocalCh, lat_hw, p.w0, in_dim, m.enc_dim, 0, (__half*)pl);
+        preproject_kernel<<<gl, 256, 0, s>>>(d.latent, kLocalCh, lat_hw, p.w3, 128 + in_dim, 128 + m.enc_dim, 1, (__half*)pl);
+        NEO_LAUNCH_CHECK("preproject_kernel(local)");
+        for (int k = 0; k < 3; ++k) {
+            void* pp = nullptr;
+            if ((rc = scene_alloc_bytes(sc, &pp, (size_t)d.nv * pl_hw * 256 * 2))) return rc;
+            m.pplane[k] = (const __half*)pp;
+            dim3 gp((pl_hw + 63) / 64, 2, d.nv);
+            preproject_kernel<<<gp, 256, 0, s>>>(planes[k], kWorldCh, pl_hw, p.w0, in_dim, m.enc_dim + kLocalCh, 0, (__half*)pp);
+            preproject_kernel<<<gp, 256, 0, s>>>(planes[k], kWorldCh, pl_hw, p.w3, 128 + in_dim, 128 + m.enc_dim + kLocalCh, 1, (__half*)pp);
+            NEO_LAUNCH_CHECK("preproject_kernel(plane)");
+        }
+    }
+    return NEO_OK;
+}
+
+void tc_scene_free(NeoScene* sc) {
+    if (sc && sc->tc_state) { delete reinterpret_cast<tc::State*>(sc->tc_state); sc->tc_state = nullptr; }
+}
+
+int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mlp_index,
+                    float* rgb, float* sigma, cudaStream_t s) {
+    using namespace tc;
+    if (!(sc->precision_mask & (1 << NEO_PREC_TC)) || !sc->tc_state) { set_error("scene was not prepared for NEO_PREC_TC"); return NEO_ERR_INVALID; }
+    const State* st = reinterpret_cast<const State*>(sc->tc_state);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        NEO_CUDA(cudaGetDevice(&dev));
+        NEO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    Params P;
+    P.rays_o = rays->rays_o; P.rays_d = rays->rays_d; P.viewdirs = rays->viewdirs; P.far = far; P.tvals = t;
+    P.ray_order = nullptr;
+    P.n_rays = rays->n_rays; P.N = N; P.chunk = rays->chunk; P.nv = sc->dev.nv;
+    P.sg = (N + kTileSamples - 1) / kTileSamples;
+    const long long groups = ((long long)rays->n_rays + kTileRays - 1) / kTileRays;
+    const long long n_tiles = groups * P.sg;
+    if (n_tiles > 0x7fffffffLL) { set_error("too many tiles"); return NEO_ERR_UNSUPPORTED; }
+    P.n_tiles = (int)n_tiles;
+    P.far_unc = 3.0f;
+    P.sc = sc->dev;
+    P.mlp = st->mlp[mlp_index];
+    P.rgb_out = rgb; P.sigma_out = sigma; P.err = sc->err_flag;
+    const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+    const size_t smem = SM_TOTAL + 1024;
+    if (mlp_index & 1) {
+        NEO_CUDA(cudaFuncSetAttribute(field_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        field_tc_kernel<4><<<grid, kThreads, smem, s>>>(P);
+    } else {
+        NEO_CUDA(cudaFuncSetAttribute(field_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        field_tc_kernel<3><<<grid, kThreads, smem, s>>>(P);
+    }
+    NEO_LAUNCH_CHECK("field_tc_kernel");
+    return NEO_OK;
+}
+
+}  // namespace neo
+
+// X (128,128) W (128,128) Wn (80,128) device fp32 -> out1 (128,128) = W X^T, out2 (128,80) = X Wn^T, fp16 operands
+extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, void* stream) {
+    using namespace neo;
+    const size_t smem = 32768 + 20480 + 64 + 1024;
+    NEO_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, W, Wn, out1, out2, nullptr);
+    NEO_LAUNCH_CHECK("selftest_kernel");
+    return NEO_OK;
 }

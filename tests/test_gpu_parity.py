@@ -240,3 +240,61 @@ def test_chunked_frame_matches_oracle_chunk_loop(cuda):
     assert orc.psnr(got["rgb"].cpu(), ref["comp_rgb"]) > 60
     # sanity: ignoring the chunk size gives a measurably different image (the quirk is real and reproduced)
     assert float((wrong["rgb"].cpu() - ref["comp_rgb"]).abs().max()) > 1e-3
+
+
+# ---------------- tensor-core path (NEO_PREC_TC) ----------------
+
+def test_tc_primitives_selftest(cuda):
+    """TS-mode tcgen05.mma (A in TMEM), SW128 K-major operand tiles, SS-mode MMA, TMEM loads -- against torch matmul
+    on the fp16-rounded operands (exact products, fp32 accumulation: tolerance 1e-3 on O(10) sums)."""
+    from neo360_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(128, 128, generator=g).to(cuda)
+    W = torch.randn(128, 128, generator=g).to(cuda)
+    Wn = torch.randn(80, 128, generator=g).to(cuda)
+    o1 = torch.zeros(128, 128, device=cuda)
+    o2 = torch.zeros(128, 80, device=cuda)
+    L.check(lib.neo_tc_selftest(L.ptr(X), L.ptr(W), L.ptr(Wn), L.ptr(o1), L.ptr(o2), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    Xh, Wh, Wnh = X.half().float(), W.half().float(), Wn.half().float()
+    assert md(o1, Wh @ Xh.T) < 1e-3
+    assert md(o2, Xh @ Wnh.T) < 1e-3
+
+
+def test_field_eval_tc_vs_oracle(cuda):
+    """TC field (fp16 operands, pre-projected features, folded head) against the oracle on identical t-values.
+    Stated tolerance: |rgb| 2e-2, sigma 2e-2 + 2% (fp16 operand rounding through a 6-layer gained MLP)."""
+    nc = 16
+    net, osc, P = make_net(cuda, (64, 48), (24, 32), nc, 8, 0, precisions=("fp32", "tc"))
+    pose = synth.target_pose(3, 100)
+    ro, vd, rd, _ = orc.rays_from_pose(orc.ray_directions(48, 64, 0.8 * 64), pose[:3, :4])
+    sel = slice(1000, 1000 + 75)                          # ragged: 75 rays -> 3 ray groups, last one partial
+    rays = {"rays_o": ro[sel].contiguous(), "rays_d": rd[sel].contiguous(), "viewdirs": vd[sel].contiguous()}
+    with torch.no_grad():
+        _, aux = orc.render(rays, osc, P, nc, 8, False, True, return_aux=True)
+    cr = {k: v.to(cuda) for k, v in rays.items()}
+    for lvl in range(2):
+        for b, (tk, rk, sk) in enumerate((("fg_t", "fg_rgb", "fg_sigma"), ("bg_s", "bg_rgb", "bg_sigma"))):
+            rgb, sig = net.field_eval(cr, aux[lvl]["far"].to(cuda), aux[lvl][tk].to(cuda), 2 * lvl + b, precision="tc")
+            net.check()
+            ds = (sig.cpu() - aux[lvl][sk]).abs()
+            assert float((ds - 0.02 * aux[lvl][sk].abs()).max()) < 2e-2, (lvl, b, float(ds.max()))
+            assert md(rgb, aux[lvl][rk]) < 2e-2, (lvl, b)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "small"])
+def test_end_to_end_tc_vs_reference_vectors(cuda, golden, tag):
+    """NEO_PREC_TC against outputs of the UNMODIFIED reference.  Stated tolerance: PSNR >= 40 dB on comp_rgb,
+    L-inf <= 3e-2 on rgb / acc / depth (fp16 tensor-core operands; resampling is driven by the fp16 coarse weights)."""
+    g = golden
+    W, H, hp, wp, B, nc, nf, seed, start = [int(x) for x in g[f"{tag}_cfg"]]
+    net, osc, P = make_net(cuda, (W, H), (hp, wp), nc, nf, seed, precisions=("tc",), precision="tc")
+    rays = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs")}
+    with torch.no_grad():
+        ev = net(rays, False, False, 0.2, 3.0, out_depth=True)
+    net.check()
+    for lvl in range(2):
+        for n_, v in zip(EV, ev[lvl]):
+            assert md(v, T(g[f"{tag}_eval{lvl}_{n_}"])) < 3e-2, (lvl, n_)
+    assert orc.psnr(ev[1][0].cpu(), T(g[f"{tag}_eval1_comp_rgb"])) > 40
