@@ -108,7 +108,26 @@ def cpu_reference_rate(sc, P, n_rays, steps=1, warmup=0, threads=None):
     chunk = 1024 as the reference's render loop; encoder hoisted.  Returns (rays/s, seconds per step list)."""
     import torch
     from oracle import neo360_oracle as orc
-    threads = threads or os.cpu_count()
+    if threads is None:
+        # eager torch on very wide hosts can be slower with every core than with a few dozen: probe and keep the best
+        threads = os.cpu_count()
+        if threads > 32:
+            best = None
+            o, d = frame_rays_cpu(0)
+            for cand in (threads, 64, 32, 16):
+                if cand > os.cpu_count():
+                    continue
+                torch.set_num_threads(cand)
+                rr = {"rays_o": o[:128].contiguous(), "rays_d": d[:128].contiguous(), "viewdirs": d[:128].contiguous()}
+                osc0 = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                                 float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    orc.render_chunked(rr, osc0, P, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+                    dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, cand)
+            threads = best[1]
     torch.set_num_threads(threads)
     osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
                     float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
