@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"])
     ap.add_argument("--precision", default=os.environ.get("NEO360_PRECISION", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--rays", type=int, default=IMG_W * IMG_H, help="debug only: fewer rays per step (not a valid headline)")
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
@@ -168,6 +168,44 @@ def main():
                                  "sample": f"{args.cpu_sample_rays} rays (one reference chunk) of frame 0 per step"},
                 "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
+        return
+
+    if args.impl == "eager-gpu":
+        # Informational: the reference ALGORITHM (oracle port = the same eager torch ops the reference issues, encoder
+        # hoisted) run on the GPU -- the stand-in for "the reference's PyTorch-GPU path" that the >=10x target names
+        # (/root/reference itself cannot travel to the GPU box).  fp32 with TF32 matmuls off and on.
+        if rank != 0:
+            return
+        import torch
+        from oracle import neo360_oracle as orc
+        dev = torch.device("cuda", local)
+        sc, P = build_scene_cpu()
+        osc = orc.Scene(*[sc[k].to(dev) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses")],
+                        float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
+        Pd = {k: v.to(dev) for k, v in P.items()}
+        o, d = frame_rays_cpu(0)
+        n = 8 * CHUNK
+        start = (IMG_H // 2) * IMG_W
+        rays = {"rays_o": o[start:start + n].to(dev), "rays_d": d[start:start + n].to(dev), "viewdirs": d[start:start + n].to(dev)}
+        res = {}
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(args.warmup):
+                    orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+                e1.record()
+                torch.cuda.synchronize()
+            res["tf32" if tf32 else "fp32"] = n * args.steps / (e0.elapsed_time(e1) * 1e-3)
+        print(json.dumps({"impl": "eager-gpu", "metric": "rays/sec at 640x480, 192 samples/ray", "unit": "rays/s",
+                          "value": res["fp32"], "value_tf32": res["tf32"], "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "config": {"workload": workload, "rays_per_step": n, "chunk": CHUNK,
+                                     "note": "oracle port (reference algorithm, eager torch ops incl. F.grid_sample) on the GPU, encoder hoisted"}}))
         return
 
     import torch

@@ -187,6 +187,10 @@ int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches
  * out2 (128,80) = X Wn^T, computed with fp16 operands / fp32 accumulation. */
 int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, void* stream);
 
+/* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 16)
+ * int64; NULL disables.  Roles and slots are documented in csrc/field_tc.cu. */
+int neo_tc_debug(long long* buf);
+
 const char* neo_last_error(void);
 /* "neo360_b200 <version> sm_100a" */
 const char* neo_version(void);

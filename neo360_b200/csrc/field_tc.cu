@@ -27,19 +27,23 @@ constexpr int kProducerWarps = 11;
 constexpr int kTileRays = 32;
 constexpr int kTileSamples = 4;
 constexpr int kTilePts = 128;
+constexpr int kHalfPts = 64;          // producer->consumer unit: half a tile (32 rays x 2 samples) x 1 view
 
 // ---- shared memory map (bytes; UMMA tiles 1024-aligned) ----
-constexpr uint32_t SM_ENC = 0;            // 128 x KE fp16, SW128 K-major, up to 2 slabs of 16 KB
+constexpr uint32_t SM_ENC = 0;            // 2 slots x (64 x KE fp16, SW128 K-major, up to 2 slabs of 8 KB)
 constexpr uint32_t SM_H = 32768;          // 128 x 128 fp16, 2 slabs
 constexpr uint32_t SM_DIR = 65536;        // 128 x 64 fp16 (32 used), 1 slab
 constexpr uint32_t SM_WHEAD = 81920;      // head weights, B operands
 constexpr uint32_t WH_H = 0, WH_DIR = 20480, WH_V1 = 30720, WH_RGB = 38912, WH_BYTES = 40960;
-constexpr uint32_t SM_G0 = 122880;        // 128 x 128 fp16 row-major
+constexpr uint32_t SM_G0 = 122880;        // 2 slots x (64 x 128 fp16 row-major)
 constexpr uint32_t SM_G3 = 155648;
-constexpr uint32_t SM_ROWTAB = 188416;    // 128 rows x 128 B
+constexpr uint32_t SM_ROWTAB = 188416;    // 2 slots x (64 rows x 128 B)
 constexpr uint32_t SM_BIAS = 204800;      // fp32: b0..b3 (512) | bq (64) | bv1 (64) | brgb (4) | bsig (1)
-constexpr uint32_t SM_BAR = 207872;
-constexpr uint32_t SM_TOTAL = 208128;
+constexpr uint32_t SM_PTS = 207872;       // per-tile cache: 128 rows x 48 B (world points are view independent)
+constexpr uint32_t SM_VIEWS = 214016;     // kMaxViews x 64 B source-camera transforms
+constexpr uint32_t SM_BAR = 214528;
+constexpr uint32_t SM_TOTAL = 214784;
+constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB = 8192;
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 
 // TMEM column map (512 columns allocated)
@@ -47,7 +51,8 @@ constexpr uint32_t TM_D = 0;        // trunk accumulator (128) ; also Dq (64) / 
 constexpr uint32_t TM_DH = 128;     // head accumulator (80)
 constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
 
-enum Bar { ENC_READY = 0, ENC_FREE, G0_READY, G0_FREE, G3_READY, G3_FREE, ACC_READY, H_READY, HEAD_READY, DIR_FREE, NUM_BARS };
+// slot-indexed barriers come in pairs (slot 0, slot 1)
+enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY, HEAD_READY, DIR_FREE, NUM_BARS };
 
 struct MlpTc {
     int in_ch, enc_dim, KE;          // 3|4, 63|84, 64|96
@@ -72,7 +77,12 @@ struct Params {
     float* rgb_out;
     float* sigma_out;
     int* err;
+    long long* dbg;     // optional [gridDim.x][16] cycle counters (neo_tc_debug), null in production
 };
+
+// cycle accounting for neo_tc_debug (one representative thread per role); compiled in, costs two CS2R when enabled
+#define TSTART() long long _t0 = clock64()
+#define TLAP(acc) do { long long _t1 = clock64(); acc += _t1 - _t0; _t0 = _t1; } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -161,6 +171,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -319,41 +335,71 @@ __global__ void head_kernel(NeoMLPParams p, int nv, unsigned char* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // the field kernel
 // ------------------------------------------------------------------------------------------------
-struct TapRow {        // 128 bytes: 4 maps x (4 texel indices, 4 weights as half2(w,w))
-    int idx[4][4];
-    uint32_t w2[4][4];
-};
 
-template <int ICH>
-__device__ __forceinline__ void write_enc_row(uint32_t enc_base, int n, const float* x) {
-    constexpr int ENC = ICH * 21, KE = (ICH == 3) ? 64 : 96;
-#pragma unroll
-    for (int c = 0; c < KE / 8; ++c) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = c * 8 + i;
-            if (e >= ENC) v[i] = 0.f;
-            else if (e < ICH) v[i] = x[e];
-            else {
-                constexpr int HALF = ICH * kPosDeg;
-                const int q0 = e - ICH;
-                const bool shifted = q0 >= HALF;
-                const int q = shifted ? q0 - HALF : q0;
-                const int k = q / ICH, cc = q % ICH;
-                float xb = x[cc] * (float)(1 << k);
-                v[i] = __sinf(shifted ? xb + 1.57079637f : xb);     // helper.py:124
-            }
-        }
-        uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        const int slab = c >> 3, cc8 = c & 7;
-        sts128(enc_base + slab * 16384 + n * 128 + ((cc8 ^ (n & 7)) << 4), pk);
+// Fast-math restatement of ray_geom / fg_point / bg_point (common.cuh) for the TC path: the results only feed fp16
+// operands and bilinear coordinates, so FMA contraction, rsqrt and approximate division are fine here.
+struct RayFast { float o[3], d[3], far, rho, phi, psph[3], axis[3]; };
+__device__ __forceinline__ void ray_fast(const float* __restrict__ o, const float* __restrict__ d, float far, RayFast& g, bool need_bg) {
+    g.o[0] = o[0]; g.o[1] = o[1]; g.o[2] = o[2]; g.d[0] = d[0]; g.d[1] = d[1]; g.d[2] = d[2]; g.far = far;
+    if (need_bg) {
+        const float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const float inv_dd = __fdividef(1.0f, dd);
+        const float d1 = -(d[0] * o[0] + d[1] * o[1] + d[2] * o[2]) * inv_dd;
+        const float p[3] = {o[0] + d1 * d[0], o[1] + d1 * d[1], o[2] + d1 * d[2]};
+        const float p2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        g.rho = sqrtf(p2);
+        const float s = d1 + sqrtf(fmaxf(1.0f - p2, 0.f)) * rsqrtf(dd);
+        for (int i = 0; i < 3; ++i) g.psph[i] = o[i] + s * d[i];
+        float ax[3] = {o[1] * g.psph[2] - o[2] * g.psph[1], o[2] * g.psph[0] - o[0] * g.psph[2], o[0] * g.psph[1] - o[1] * g.psph[0]};
+        const float an = rsqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        for (int i = 0; i < 3; ++i) g.axis[i] = ax[i] * an;
+        g.phi = asinf(g.rho);
     }
 }
+__device__ __forceinline__ void bg_point_fast(const RayFast& g, float s, float far_unc, float* xhat, float* lin) {
+    const float ang = g.phi - asinf(g.rho * s);
+    float sa, ca;
+    __sincosf(ang, &sa, &ca);
+    const float* a = g.axis;
+    const float* p = g.psph;
+    const float cr[3] = {a[1] * p[2] - a[2] * p[1], a[2] * p[0] - a[0] * p[2], a[0] * p[1] - a[1] * p[0]};
+    const float ap = (a[0] * p[0] + a[1] * p[1] + a[2] * p[2]) * (1.0f - ca);
+    float q[3];
+    for (int i = 0; i < 3; ++i) q[i] = p[i] * ca + cr[i] * sa + a[i] * ap;
+    const float qn = __fdividef(1.0f, sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) + 1e-10f);
+    for (int i = 0; i < 3; ++i) xhat[i] = q[i] * qn;
+    const float tl = g.far * (1.0f - s) + far_unc * s;
+    for (int i = 0; i < 3; ++i) lin[i] = g.o[i] + tl * g.d[i];
+}
 
-__device__ __forceinline__ void taps_to_row(const Taps& t, int (&idx)[4], uint32_t (&w2)[4]) {
+struct PtsRow {        // 48 bytes: view-independent per-row data, computed once per tile
+    float xe[3];       // point fed to the positional encoding (fg: sample point, bg: unit-sphere point)
+    float tv;          // t (fg) or inverse radius s (bg)
+    float xl[3];       // lookup point (fg: same point, bg: far(1-s)+3s along the ray, quirk Q2)
+    int pad[5];
+};
+
+// one positional-encoding chunk (8 consecutive K elements) of row `x`
+template <int ICH>
+__device__ __forceinline__ uint4 enc_chunk(int c, const float* x) {
+    constexpr int ENC = ICH * 21;
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { idx[i] = t.idx[i]; w2[i] = pack_h2(t.w[i], t.w[i]); }
+    for (int i = 0; i < 8; ++i) {
+        const int e = c * 8 + i;
+        if (e >= ENC) v[i] = 0.f;
+        else if (e < ICH) v[i] = x[e];
+        else {
+            constexpr int HALF = ICH * kPosDeg;
+            const int q0 = e - ICH;
+            const bool shifted = q0 >= HALF;
+            const int q = shifted ? q0 - HALF : q0;
+            const int k = q / ICH, cc = q % ICH;
+            const float xb = x[cc] * (float)(1 << k);
+            v[i] = __sinf(shifted ? xb + 1.57079637f : xb);     // helper.py:124
+        }
+    }
+    return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
 
 template <int ICH>
@@ -370,12 +416,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
-        mbar_init(BAR(ENC_READY), kProducerWarps * 32);
-        mbar_init(BAR(ENC_FREE), 1);
-        mbar_init(BAR(G0_READY), kProducerWarps * 32);
-        mbar_init(BAR(G0_FREE), 128);
-        mbar_init(BAR(G3_READY), kProducerWarps * 32);
-        mbar_init(BAR(G3_FREE), 128);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(BAR(ENC_READY + s), kProducerWarps * 32);
+            mbar_init(BAR(ENC_FREE + s), 1);
+            mbar_init(BAR(G_READY + s), kProducerWarps * 32);
+            mbar_init(BAR(G_FREE + s), 128);
+        }
         mbar_init(BAR(ACC_READY), 1);
         mbar_init(BAR(H_READY), 128);
         mbar_init(BAR(HEAD_READY), 1);
@@ -388,6 +434,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         for (int i = threadIdx.x; i < (int)(WH_BYTES / 16); i += kThreads) sts128(sbase + SM_WHEAD + 16 * i, __ldg(src + i));
         float* bsm = reinterpret_cast<float*>(sgen + SM_BIAS);
         for (int i = threadIdx.x; i < BIAS_FLOATS; i += kThreads) bsm[i] = __ldg(P.mlp.bias + i);
+        float* vsm = reinterpret_cast<float*>(sgen + SM_VIEWS);
+        const float* vsrc = reinterpret_cast<const float*>(P.sc.views);
+        for (int i = threadIdx.x; i < P.nv * 16; i += kThreads) vsm[i] = __ldg(vsrc + i);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -411,174 +460,241 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
     tc_fence_after();
 
     const int nv = P.nv, N = P.N;
-    const long long total_pts = (long long)P.n_rays * N;
-    (void)total_pts;
 
     if (warp >= kProducerWarp0) {
         // =====================================================================================
-        // PRODUCERS: geometry + positional encoding + tap tables, then the two gather passes
+        // PRODUCERS.  Unit of work: half-job (tile, view, half) = 64 points of one view, double-buffered slots.
         // =====================================================================================
         const int pw = warp - kProducerWarp0, ptid = threadIdx.x - kProducerWarp0 * 32;
-        uint32_t ph_enc_free = 1, ph_g0_free = 1, ph_g3_free = 1, ph_dir_free = 1;
-        const uint32_t rowtab = sbase + SM_ROWTAB;
+        uint32_t ph_dir_free = 1;
+        uint32_t kcount = 0;
+        long long tp_pts = 0, tp_encwait = 0, tp_geom = 0, tp_gwait = 0, tp_gather = 0, tp_bar = 0;
+        TSTART();
+        PtsRow* pts = reinterpret_cast<PtsRow*>(sgen + SM_PTS);
+        const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
+        const size_t lat_hw = (size_t)P.sc.lat_h * P.sc.lat_w, pl_hw = (size_t)P.sc.plane_h * P.sc.plane_w;
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
-                // all producer warps must be done reading ROWTAB of the previous job
-                asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
-                mbar_wait(BAR(ENC_FREE), ph_enc_free, P.err, 1); ph_enc_free ^= 1;
-                if (v == 0) { mbar_wait(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
-                if (ptid < kTilePts) {
-                    const int n = ptid, rl = n & 31, sl = n >> 5;
-                    const int slot = min(g * kTileRays + rl, P.n_rays - 1);
-                    const int rid = P.ray_order ? P.ray_order[slot] : slot;
-                    const int s = min(q * kTileSamples + sl, N - 1);
-                    RayGeom rg;
-                    ray_geom(P.rays_o + 3 * rid, P.rays_d + 3 * rid, rg, IS_BG);
-                    rg.far = P.far[rid];
-                    const float tv = P.tvals[(long long)rid * N + s];
-                    float xe[3], xl[3];
-                    if (IS_BG) bg_point(rg, tv, P.far_unc, xe, xl);
-                    else { fg_point(rg, tv, xe); xl[0] = xe[0]; xl[1] = xe[1]; xl[2] = xe[2]; }
-                    const ViewXform vx = P.sc.views[v];
-                    float ce[4], cl[3];
-                    to_camera(vx, xe, ce);
-                    to_camera(vx, xl, cl);
-                    ce[3] = tv;
-                    write_enc_row<ICH>(sbase + SM_ENC, n, ce);
-                    TapRow tr;
-                    Taps tp;
-                    float gx, gy;
-                    local_grid_coords(P.sc, cl, gx, gy);
-                    bilinear_taps(gx, gy, P.sc.lat_w, P.sc.lat_h, tp); taps_to_row(tp, tr.idx[0], tr.w2[0]);
-                    bilinear_taps(cl[0], cl[2], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[1], tr.w2[1]);
-                    bilinear_taps(cl[0], cl[1], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[2], tr.w2[2]);
-                    bilinear_taps(cl[1], cl[2], P.sc.plane_w, P.sc.plane_h, tp); taps_to_row(tp, tr.idx[3], tr.w2[3]);
-                    const uint4* trv = reinterpret_cast<const uint4*>(&tr);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sts128(rowtab + n * 128 + 16 * i, trv[i]);
+                for (int h = 0; h < 2; ++h, ++kcount) {
+                    const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
+                    const uint32_t rowtab = sbase + SM_ROWTAB + slot * SLOT_TAB;
+                    const uint32_t encb = sbase + SM_ENC + slot * SLOT_ENC;
                     if (v == 0) {
-                        // mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360)
-                        const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
-                        const int c0 = (rid / ch) * ch;
-                        const int Bc = min(ch, P.n_rays - c0);
-                        const long long jl = (long long)(rid - c0) * N + s;
-                        const int src = c0 + (int)(jl % Bc);
-                        const float* wd = P.viewdirs + 3 * src;
-                        float acc[32];
+                        // ---- per-tile, view-independent: world points + mean direction encoding (rows 64h..64h+63) ----
+                        if (h == 0) { mbar_wait(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
+                        if (ptid < 4 * kHalfPts) {
+                            // 4 threads per row: sub 0 = world points, sub 1..3 = direction encodings of the views (summed by shuffles)
+                            const int row = ptid >> 2, sub = ptid & 3;
+                            const int n = h * kHalfPts + row, rl = n & 31, sl = n >> 5;
+                            const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
+                            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
+                            const int s = min(q * kTileSamples + sl, N - 1);
+                            float acc[28];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                        for (int vv = 0; vv < nv; ++vv) {
-                            float dc[3];
-                            rotate_to_camera(P.sc.views[vv], wd, dc);
-#pragma unroll
-                            for (int i = 0; i < kDirEnc; ++i) {
-                                float val;
-                                if (i < 3) val = dc[i];
+                            for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+                            if (sub == 0) {
+                                const float fr = P.far[rid];
+                                const float tv = P.tvals[(long long)rid * N + s];
+                                RayFast rg;
+                                ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
+                                PtsRow pr;
+                                pr.tv = tv;
+                                if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
                                 else {
-                                    const int q0 = i - 3;
-                                    const bool shifted = q0 >= 12;
-                                    const int qq = shifted ? q0 - 12 : q0;
-                                    const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
-                                    val = __sinf(shifted ? xb + 1.57079637f : xb);
+                                    for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
                                 }
-                                acc[i] += val;
+                                pts[n] = pr;
+                            } else {
+                                // direction encoding of the quirk-Q1 conditioning ray (model.py:357-360), views sub-1, sub+2, ...
+                                const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
+                                const int c0 = (rid / ch) * ch;
+                                const int Bc = min(ch, P.n_rays - c0);
+                                const long long jl = (long long)(rid - c0) * N + s;
+                                const int src = c0 + ((jl < 0x7fffffffLL) ? (int)((unsigned)jl % (unsigned)Bc) : (int)(jl % Bc));
+                                const float wd[3] = {P.viewdirs[3 * src], P.viewdirs[3 * src + 1], P.viewdirs[3 * src + 2]};
+                                for (int vv = sub - 1; vv < nv; vv += 3) {
+                                    float dc[3];
+                                    rotate_to_camera(vxs[vv], wd, dc);
+#pragma unroll
+                                    for (int i = 0; i < kDirEnc; ++i) {
+                                        float val;
+                                        if (i < 3) val = dc[i];
+                                        else {
+                                            const int q0 = i - 3;
+                                            const bool shifted = q0 >= 12;
+                                            const int qq = shifted ? q0 - 12 : q0;
+                                            const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
+                                            val = __sinf(shifted ? xb + 1.57079637f : xb);
+                                        }
+                                        acc[i] += val;
+                                    }
+                                }
+                            }
+                            const float inv = 1.0f / (float)nv;
+#pragma unroll
+                            for (int i = 0; i < 28; ++i) {
+                                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+                                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+                                acc[i] *= inv;
+                            }
+                            // each of the 4 threads writes one 16-byte chunk (8 of the 32 K columns, 27 used) of the DIR row
+                            float e8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float x = 0.f;
+#pragma unroll
+                                for (int c2 = 0; c2 < 4; ++c2) { const int idx = c2 * 8 + i; if (sub == c2 && idx < 28) x = acc[idx < 28 ? idx : 0]; }
+                                e8[i] = x;
+                            }
+                            sts128(sbase + SM_DIR + n * 128 + ((sub ^ (n & 7)) << 4),
+                                   make_uint4(pack_h2(e8[0], e8[1]), pack_h2(e8[2], e8[3]), pack_h2(e8[4], e8[5]), pack_h2(e8[6], e8[7])));
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));    // PTS visible to all producer threads
+                        TLAP(tp_pts);
+                    }
+                    // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved) ----
+                    mbar_wait(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
+                    TLAP(tp_encwait);
+                    if (ptid < 4 * kHalfPts) {
+                        const int row = ptid >> 2, sub = ptid & 3;
+                        const PtsRow pr = pts[h * kHalfPts + row];
+                        const ViewXform vx = vxs[v];
+                        float ce[4], cl[3];
+                        to_camera(vx, pr.xe, ce);
+                        to_camera(vx, pr.xl, cl);
+                        ce[3] = pr.tv;
+                        Taps tp;
+                        if (sub == 0) {
+                            float gx, gy;
+                            local_grid_coords(P.sc, cl, gx, gy);
+                            bilinear_taps(gx, gy, P.sc.lat_w, P.sc.lat_h, tp);
+                        } else {
+                            const float ga = (sub == 3) ? cl[1] : cl[0];
+                            const float gb = (sub == 2) ? cl[1] : cl[2];          // xz, xy, yz
+                            bilinear_taps(ga, gb, P.sc.plane_w, P.sc.plane_h, tp);
+                        }
+                        // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w)
+                        sts128(rowtab + row * 128 + sub * 32, make_uint4(tp.idx[0] * 32, tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
+                        sts128(rowtab + row * 128 + sub * 32 + 16, make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
+                                                                               pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
+#pragma unroll
+                        for (int c = 0; c < KE / 8; ++c) {
+                            if ((c & 3) == sub) {
+                                const uint4 pk = enc_chunk<ICH>(c, ce);
+                                sts128(encb + (c >> 3) * SLAB_ENC + row * 128 + (((c & 7) ^ (row & 7)) << 4), pk);
                             }
                         }
-                        const float inv = 1.0f / (float)nv;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 pk = make_uint4(pack_h2(acc[8 * c] * inv, acc[8 * c + 1] * inv), pack_h2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
-                                                  pack_h2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv), pack_h2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
-                            sts128(sbase + SM_DIR + n * 128 + ((c ^ (n & 7)) << 4), pk);
-                        }
                     }
-                }
-                fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
-                mbar_arrive(BAR(ENC_READY));
-                asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB complete
-                // ---- gather passes: G0 (layer-0 features) then G3 (layer-3 features) ----
-                const size_t lat_hw = (size_t)P.sc.lat_h * P.sc.lat_w, pl_hw = (size_t)P.sc.plane_h * P.sc.plane_w;
-                const __half* mapbase[4] = {P.mlp.plocal + (size_t)v * lat_hw * 256, P.mlp.pplane[0] + (size_t)v * pl_hw * 256,
-                                            P.mlp.pplane[1] + (size_t)v * pl_hw * 256, P.mlp.pplane[2] + (size_t)v * pl_hw * 256};
+                    fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
+                    mbar_arrive(BAR(ENC_READY + slot));
+                    TLAP(tp_geom);
+                    asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB[slot] complete
+                    TLAP(tp_bar);
+                    // ---- gather: one pass, 16 taps x 512 B per row; lanes 0-15 carry the layer-0 half, 16-31 the layer-3 half ----
+                    {
+                        const uint4* mapbase[4];
+                        mapbase[0] = reinterpret_cast<const uint4*>(P.mlp.plocal + (size_t)v * lat_hw * 256) + lane;
+#pragma unroll
+                        for (int m = 1; m < 4; ++m)
+                            mapbase[m] = reinterpret_cast<const uint4*>(P.mlp.pplane[m - 1] + (size_t)v * pl_hw * 256) + lane;
+                        mbar_wait(BAR(G_FREE + slot), use ^ 1, P.err, 3);
+                        TLAP(tp_gwait);
+                        const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + (lane & 15) * 16;
 #pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (pass == 0) { mbar_wait(BAR(G0_FREE), ph_g0_free, P.err, 3); ph_g0_free ^= 1; }
-                    else { mbar_wait(BAR(G3_FREE), ph_g3_free, P.err, 4); ph_g3_free ^= 1; }
-                    const uint32_t gdst = sbase + (pass == 0 ? SM_G0 : SM_G3);
-#pragma unroll 1
-                    for (int r = pw; r < kTilePts; r += kProducerWarps) {
-                        uint4 tb[8];
+                        for (int r = pw; r < kHalfPts; r += kProducerWarps) {
+                            uint4 val[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) tb[i] = lds128(rowtab + r * 128 + 16 * i);
-                        const int* ti = reinterpret_cast<const int*>(&tb[0]);        // idx[4][4]
-                        const uint32_t* tw = reinterpret_cast<const uint32_t*>(&tb[4]);   // w2[4][4]
-                        uint2 val[16];
-#pragma unroll
-                        for (int m = 0; m < 4; ++m)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                val[m * 4 + k] = __ldg(reinterpret_cast<const uint2*>(mapbase[m] + (size_t)ti[m * 4 + k] * 256 + pass * 128) + lane);
-                        float f[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const __half2 w = *reinterpret_cast<const __half2*>(&tw[m * 4 + k]);
-                                a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&val[m * 4 + k].x), a0);
-                                a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&val[m * 4 + k].y), a1);
+                            for (int m = 0; m < 4; ++m) {
+                                const uint4 off = lds128(rowtab + r * 128 + m * 32);
+                                val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
+                                val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
+                                val[m * 4 + 2] = __ldg(mapbase[m] + off.z);
+                                val[m * 4 + 3] = __ldg(mapbase[m] + off.w);
                             }
-                            const float2 x0 = __half22float2(a0), x1 = __half22float2(a1);
-                            f[0] += x0.x; f[1] += x0.y; f[2] += x1.x; f[3] += x1.y;
+                            __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                const uint4 wq = lds128(rowtab + r * 128 + m * 32 + 16);
+                                const uint32_t wv[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __half2 w = *reinterpret_cast<const __half2*>(&wv[k]);
+                                    const uint4& x = val[m * 4 + k];
+                                    a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.x), a0);
+                                    a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.y), a1);
+                                    a2 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.z), a2);
+                                    a3 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.w), a3);
+                                }
+                            }
+                            sts128(gdst + r * 256, make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
+                                                              *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3)));
                         }
-                        sts64(gdst + r * 256 + lane * 8, make_uint2(pack_h2(f[0], f[1]), pack_h2(f[2], f[3])));
+                        mbar_arrive(BAR(G_READY + slot));
+                        TLAP(tp_gather);
                     }
-                    mbar_arrive(BAR(pass == 0 ? G0_READY : G3_READY));
                 }
             }
+        }
+        if (P.dbg && ptid == 0) {
+            long long* d = P.dbg + (size_t)blockIdx.x * 16;
+            d[0] = tp_pts; d[1] = tp_encwait; d[2] = tp_geom; d[3] = tp_bar; d[4] = tp_gwait; d[5] = tp_gather;
         }
     } else if (warp == 4) {
         // =====================================================================================
         // MMA ISSUE (one thread)
         // =====================================================================================
         if (lane == 0) {
-            uint32_t ph_enc = 0, ph_h = 0;
-            const uint32_t id_trunk = idesc_f16(128, 128), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
+            uint32_t ph_h = 0, kcount = 0;
+            long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0;
+            TSTART();
+            const uint32_t id_trunk = idesc_f16(128, kHalfPts), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
             const uint32_t dD = tmem + TM_D, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
-            const uint32_t sENC = sbase + SM_ENC, sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
+            const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
             for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
                 for (int v = 0; v < nv; ++v) {
-                    mbar_wait(BAR(ENC_READY), ph_enc, P.err, 10); ph_enc ^= 1;
-                    tc_fence_after();
-                    // L0: D = W0enc . ENC^T
-#pragma unroll
-                    for (int ks = 0; ks < KE / 16; ++ks)
-                        mma_ts(dD, aW0 + ks * 8, desc_sw128(kaddr(sENC, ks, 16384)), id_trunk, ks > 0);
-                    tc_commit(BAR(ACC_READY));
-                    // L1, L2
-                    for (int l = 1; l <= 2; ++l) {
-                        mbar_wait(BAR(H_READY), ph_h, P.err, 11); ph_h ^= 1;
+                    for (int h = 0; h < 2; ++h, ++kcount) {
+                        const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
+                        const uint32_t sENC = sbase + SM_ENC + slot * SLOT_ENC;
+                        const uint32_t sHh = sH + h * (kHalfPts * 128);        // rows 64h.. of each 128-row slab
+                        TLAP(tm_issue);
+                        mbar_wait(BAR(ENC_READY + slot), use, P.err, 10);
+                        TLAP(tm_encwait);
                         tc_fence_after();
-                        const uint32_t aW = (l == 1) ? aW1 : aW2;
+                        // L0: D[:, 0:64] = W0enc . ENC^T
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW + ks * 8, desc_sw128(kaddr(sH, ks, 16384)), id_trunk, ks > 0);
+                        for (int ks = 0; ks < KE / 16; ++ks)
+                            mma_ts(dD, aW0 + ks * 8, desc_sw128(kaddr(sENC, ks, SLAB_ENC)), id_trunk, ks > 0);
                         tc_commit(BAR(ACC_READY));
+                        for (int l = 1; l <= 2; ++l) {
+                            TLAP(tm_issue);
+                            mbar_wait(BAR(H_READY), ph_h, P.err, 11); ph_h ^= 1;
+                            TLAP(tm_hwait);
+                            tc_fence_after();
+                            const uint32_t aW = (l == 1) ? aW1 : aW2;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW + ks * 8, desc_sw128(kaddr(sHh, ks, 16384)), id_trunk, ks > 0);
+                            tc_commit(BAR(ACC_READY));
+                        }
+                        // L3: D = W3h . H^T + W3enc . ENC^T
+                        TLAP(tm_issue);
+                        mbar_wait(BAR(H_READY), ph_h, P.err, 12); ph_h ^= 1;
+                        TLAP(tm_hwait);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW3h + ks * 8, desc_sw128(kaddr(sHh, ks, 16384)), id_trunk, ks > 0);
+#pragma unroll
+                        for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW3e + ks * 8, desc_sw128(kaddr(sENC, ks, SLAB_ENC)), id_trunk, 1);
+                        tc_commit(BAR(ACC_READY));
+                        tc_commit(BAR(ENC_FREE + slot));
+                        TLAP(tm_issue);
+                        mbar_wait(BAR(H_READY), ph_h, P.err, 13); ph_h ^= 1;      // h3 of this half written
+                        TLAP(tm_hwait);
+                        tc_fence_after();
                     }
-                    // L3: D = W3h . H^T + W3enc . ENC^T
-                    mbar_wait(BAR(H_READY), ph_h, P.err, 12); ph_h ^= 1;
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW3h + ks * 8, desc_sw128(kaddr(sH, ks, 16384)), id_trunk, ks > 0);
-#pragma unroll
-                    for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW3e + ks * 8, desc_sw128(kaddr(sENC, ks, 16384)), id_trunk, 1);
-                    tc_commit(BAR(ACC_READY));
-                    tc_commit(BAR(ENC_FREE));
-                    // head: Dh (+)= H3 . (Whead_h)^T      (points on lanes, accumulates the view mean)
-                    mbar_wait(BAR(H_READY), ph_h, P.err, 13); ph_h ^= 1;
-                    tc_fence_after();
+                    // head: Dh (+)= H3 . (Whead_h)^T      (128 points on lanes, accumulates the view mean)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         mma_ss(dH, desc_sw128(kaddr(sH, ks, 16384)), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
@@ -605,6 +721,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 mbar_wait(BAR(H_READY), ph_h, P.err, 16); ph_h ^= 1;
                 tc_fence_after();
             }
+            if (P.dbg) {
+                long long* d = P.dbg + (size_t)blockIdx.x * 16;
+                d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue;
+            }
         }
     } else {
         // =====================================================================================
@@ -612,7 +732,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         // =====================================================================================
         const int c = warp * 32 + lane;                 // neuron (trunk) / point row (head)
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ph_acc = 0, ph_g0 = 0, ph_g3 = 0, ph_head = 0;
+        uint32_t ph_acc = 0, ph_head = 0, kcount = 0;
+        long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
+        TSTART();
         uint32_t hoff[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) hoff[j] = (uint32_t)(c >> 6) * 16384u + (uint32_t)(((((c & 63) >> 3) ^ j) << 4) + (c & 7) * 2);
@@ -620,40 +742,48 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
+                for (int h = 0; h < 2; ++h, ++kcount) {
+                    const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
+                    const uint32_t sHh = sH + h * (kHalfPts * 128);
 #pragma unroll 1
-                for (int l = 0; l < 4; ++l) {
-                    const float bias = lds_f32(sBias + 4 * (l * 128 + c));
-                    mbar_wait(BAR(ACC_READY), ph_acc, P.err, 20 + l); ph_acc ^= 1;
-                    tc_fence_after();
-                    uint32_t gsrc = 0;
-                    if (l == 0) { mbar_wait(BAR(G0_READY), ph_g0, P.err, 24); ph_g0 ^= 1; gsrc = sbase + SM_G0 + c * 2; }
-                    if (l == 3) { mbar_wait(BAR(G3_READY), ph_g3, P.err, 25); ph_g3 ^= 1; gsrc = sbase + SM_G3 + c * 2; }
+                    for (int l = 0; l < 4; ++l) {
+                        const float bias = lds_f32(sBias + 4 * (l * 128 + c));
+                        TLAP(te_work);
+                        mbar_wait(BAR(ACC_READY), ph_acc, P.err, 20 + l); ph_acc ^= 1;
+                        TLAP(te_accwait);
+                        tc_fence_after();
+                        uint32_t gsrc = 0;
+                        if (l == 0) { mbar_wait(BAR(G_READY + slot), use, P.err, 24); gsrc = sbase + SM_G0 + slot * SLOT_G + c * 2; TLAP(te_gwait); }
+                        if (l == 3) gsrc = sbase + SM_G3 + slot * SLOT_G + c * 2;
+                        const __half* gp = reinterpret_cast<const __half*>(sgen + (gsrc - sbase));      // G[slot][0][c]
+                        unsigned char* hp = sgen + (sHh - sbase);
 #pragma unroll 1
-                    for (int cb = 0; cb < 4; ++cb) {
-                        uint32_t r[32];
-                        tmem_ld32(lane_base + TM_D + cb * 32, r);
-                        tc_wait_ld();
+                        for (int cb = 0; cb < kHalfPts / 8; ++cb) {
+                            float gv[8];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int n = cb * 32 + i;
-                            float x = __uint_as_float(r[i]) + bias;
-                            if (gsrc) x += __half2float(__ushort_as_half(lds16(gsrc + n * 256)));
-                            x = fmaxf(x, 0.f);
-                            sts16(sH + n * 128 + hoff[i & 7], __half_as_ushort(__float2half_rn(x)));
+                            for (int i = 0; i < 8; ++i) gv[i] = gsrc ? __half2float(gp[(cb * 8 + i) * 128]) : 0.f;
+                            uint32_t r[8];
+                            tmem_ld8(lane_base + TM_D + cb * 8, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float x = fmaxf(__uint_as_float(r[i]) + bias + gv[i], 0.f);
+                                *reinterpret_cast<__half*>(hp + (cb * 8 + i) * 128 + hoff[i]) = __float2half_rn(x);
+                            }
                         }
+                        if (l == 3) mbar_arrive(BAR(G_FREE + slot));
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(BAR(H_READY));
                     }
-                    if (l == 0) mbar_arrive(BAR(G0_FREE));
-                    if (l == 3) mbar_arrive(BAR(G3_FREE));
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(BAR(H_READY));
                 }
             }
             // ---- head epilogue: thread = point row c ----
+            TLAP(te_work);
             const int rl = c & 31, sl = c >> 5;
-            const int slot = g * kTileRays + rl, s = q * kTileSamples + sl;
-            const bool valid = slot < P.n_rays && s < N;
-            const int rid = P.ray_order ? P.ray_order[min(slot, P.n_rays - 1)] : min(slot, P.n_rays - 1);
+            const int slot_r = g * kTileRays + rl, s = q * kTileSamples + sl;
+            const bool valid = slot_r < P.n_rays && s < N;
+            const int rid = P.ray_order ? P.ray_order[min(slot_r, P.n_rays - 1)] : min(slot_r, P.n_rays - 1);
             const long long gp = (long long)rid * N + min(s, N - 1);
             mbar_wait(BAR(HEAD_READY), ph_head, P.err, 26); ph_head ^= 1;
             tc_fence_after();
@@ -707,6 +837,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 }
             }
             tc_fence_before(); mbar_arrive(BAR(H_READY));
+            TLAP(te_head);
+        }
+        if (P.dbg && threadIdx.x == 0) {
+            long long* d = P.dbg + (size_t)blockIdx.x * 16;
+            d[9] = te_accwait; d[10] = te_gwait; d[11] = te_work; d[12] = te_head;
         }
     }
     // ---- teardown ----
@@ -839,6 +974,8 @@ void tc_scene_free(NeoScene* sc) {
     if (sc && sc->tc_state) { delete reinterpret_cast<tc::State*>(sc->tc_state); sc->tc_state = nullptr; }
 }
 
+static long long* g_dbg = nullptr;   // set by neo_tc_debug
+
 int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mlp_index,
                     float* rgb, float* sigma, cudaStream_t s) {
     using namespace tc;
@@ -863,6 +1000,7 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
     P.sc = sc->dev;
     P.mlp = st->mlp[mlp_index];
     P.rgb_out = rgb; P.sigma_out = sigma; P.err = sc->err_flag;
+    P.dbg = g_dbg;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
     const size_t smem = SM_TOTAL + 1024;
     if (mlp_index & 1) {
@@ -887,3 +1025,8 @@ extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, 
     NEO_LAUNCH_CHECK("selftest_kernel");
     return NEO_OK;
 }
+
+// Debug: cycle accounting of the TC field kernel.  buf = device array of 148*16 int64 (zeroed by the caller) or NULL to disable.
+// Per CTA: [0] pts [1] wait ENC_FREE [2] geometry [3] producer bar [4] wait G_FREE [5] gather | [6] MMA wait ENC_READY
+// [7] MMA wait H_READY [8] MMA issue | [9] epi wait ACC [10] epi wait G [11] epi work [12] epi head
+extern "C" int neo_tc_debug(long long* buf) { neo::g_dbg = buf; return NEO_OK; }

@@ -108,7 +108,7 @@ def _jitter(t: Tensor, u_rand: Tensor) -> Tensor:
 
 def sample_fg(o, d, n, near, far, u_rand: Optional[Tensor] = None):
     """in_sphere=True branch.  u_rand (B,n+1) replaces torch.rand (helper.py:50) when randomized."""
-    u = torch.linspace(0.0, 1.0, n + 1)
+    u = torch.linspace(0.0, 1.0, n + 1, device=o.device)
     t = near * (1.0 - u) + far * u
     if u_rand is not None:
         t = _jitter(t, u_rand)
@@ -121,7 +121,7 @@ def sample_fg(o, d, n, near, far, u_rand: Optional[Tensor] = None):
 def sample_bg(o, d, n, far, far_unc=3.0, u_rand: Optional[Tensor] = None):
     """in_sphere=False branch: s descends 1->0; `lin` are the farthest-first lookup points (quirk Q2)."""
     B = o.shape[0]
-    s = torch.broadcast_to(torch.linspace(0.0, 1.0, n + 1), (B, n + 1))
+    s = torch.broadcast_to(torch.linspace(0.0, 1.0, n + 1, device=o.device), (B, n + 1))
     if u_rand is not None:
         s = _jitter(s, u_rand)
     t_lin = far * (1.0 - s) + far_unc * s
@@ -150,7 +150,7 @@ def piecewise_constant_pdf(bins: Tensor, w: Tensor, m: int, u_rand: Optional[Ten
     if u_rand is not None:
         u = u_rand
     else:
-        u = torch.linspace(0.0, 1.0 - 2 ** -32, m)  # endpoint rounds to 1.0 in fp32 (quirk Q7)
+        u = torch.linspace(0.0, 1.0 - 2 ** -32, m, device=w.device)  # endpoint rounds to 1.0 in fp32 (quirk Q7)
         u = torch.broadcast_to(u, (*cdf.shape[:-1], m))
     mask = u[..., None, :] >= cdf[..., :, None]
 
@@ -259,11 +259,12 @@ def triplane_lookup(p_cam: Tensor, sc: Scene, impl="explicit") -> Tensor:
 def local_lookup(p_cam: Tensor, sc: Scene, impl="explicit") -> Tensor:
     """get_local_feats (model.py:239-264) -> projection (util.py:92-111) -> index (encoder_pn.py:101-152)."""
     uv = -p_cam[..., :2] / (p_cam[..., 2:] + 1e-9)
-    uv = uv * torch.tensor([sc.focal, -sc.focal]) + torch.tensor([sc.cx, sc.cy])
+    dev = p_cam.device
+    uv = uv * torch.tensor([sc.focal, -sc.focal], device=dev) + torch.tensor([sc.cx, sc.cy], device=dev)
     Hl, Wl = sc.latent.shape[-2:]
-    ls = torch.tensor([float(Wl), float(Hl)])
+    ls = torch.tensor([float(Wl), float(Hl)], device=dev)
     ls = ls / (ls - 1) * 2.0
-    scale = ls / torch.tensor([float(sc.img_w), float(sc.img_h)])
+    scale = ls / torch.tensor([float(sc.img_w), float(sc.img_h)], device=dev)
     uv = uv * scale - 1.0
     return bilinear_zeros(sc.latent, uv[..., 0], uv[..., 1], impl)
 
@@ -274,7 +275,7 @@ def local_lookup(p_cam: Tensor, sc: Scene, impl="explicit") -> Tensor:
 
 
 def pos_enc(x: Tensor, min_deg: int, max_deg: int) -> Tensor:
-    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)], dtype=x.dtype)
+    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)], dtype=x.dtype, device=x.device)
     xb = (x[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], -1)
     return torch.cat([x, torch.sin(torch.cat([xb, xb + 0.5 * math.pi], -1))], -1)
 
