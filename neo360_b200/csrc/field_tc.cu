@@ -52,7 +52,9 @@ constexpr uint32_t TM_DH = 128;     // head accumulator (80)
 constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
 
 // slot-indexed barriers come in pairs (slot 0, slot 1)
-enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY, HEAD_READY, DIR_FREE, NUM_BARS };
+// ACC_READY / H_READY are indexed by the 32-point block (0/1) of the half-job: the two blocks ping-pong between the
+// tensor core and the epilogue warps, so MMA latency hides behind the other block's epilogue.
+enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY = 10, HEAD_READY = 12, DIR_FREE, NUM_BARS };
 
 struct MlpTc {
     int in_ch, enc_dim, KE;          // 3|4, 63|84, 64|96
@@ -95,6 +97,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// whole-warp arrival: every lane has finished (and fenced) its writes, one lane signals
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -114,6 +121,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
             __trap();
         }
     }
+}
+// one lane of a fully converged warp (the MMA warp keeps warp-uniform control flow so descriptors stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -417,13 +430,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(BAR(ENC_READY + s), kProducerWarps * 32);
+            mbar_init(BAR(ENC_READY + s), kProducerWarps);        // one elected arrival per warp
             mbar_init(BAR(ENC_FREE + s), 1);
-            mbar_init(BAR(G_READY + s), kProducerWarps * 32);
-            mbar_init(BAR(G_FREE + s), 128);
+            mbar_init(BAR(G_READY + s), kProducerWarps);
+            mbar_init(BAR(G_FREE + s), 4);
         }
         mbar_init(BAR(ACC_READY), 1);
-        mbar_init(BAR(H_READY), 128);
+        mbar_init(BAR(ACC_READY + 1), 1);
+        mbar_init(BAR(H_READY), 4);
+        mbar_init(BAR(H_READY + 1), 4);
         mbar_init(BAR(HEAD_READY), 1);
         mbar_init(BAR(DIR_FREE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -481,83 +496,87 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     const uint32_t rowtab = sbase + SM_ROWTAB + slot * SLOT_TAB;
                     const uint32_t encb = sbase + SM_ENC + slot * SLOT_ENC;
                     if (v == 0) {
-                        // ---- per-tile, view-independent: world points + mean direction encoding (rows 64h..64h+63) ----
+                        // ---- per-tile, view-independent world points of rows 64h..64h+63 (one thread per row) ----
+                        if (ptid < kHalfPts) {
+                            const int n = h * kHalfPts + ptid, rl = n & 31, sl = n >> 5;
+                            const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
+                            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
+                            const int s = min(q * kTileSamples + sl, N - 1);
+                            const float fr = P.far[rid];
+                            const float tv = P.tvals[(long long)rid * N + s];
+                            RayFast rg;
+                            ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
+                            PtsRow pr;
+                            pr.tv = tv;
+                            if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
+                            else {
+                                for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
+                            }
+                            pts[n] = pr;
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));    // PTS visible to all producer threads
+                        TLAP(tp_pts);
+                    }
+                    if (v == nv - 1) {
+                        // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360);
+                        //      written with the LAST view so the previous tile's head MMA has long released the DIR tile ----
                         if (h == 0) { mbar_wait(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
-                        if (ptid < 4 * kHalfPts) {
-                            // 4 threads per row: sub 0 = world points, sub 1..3 = direction encodings of the views (summed by shuffles)
-                            const int row = ptid >> 2, sub = ptid & 3;
+                        const int dt = ptid - (kProducerWarps * 32 - 4 * 32);       // last 4 producer warps: 128 threads = 64 rows x 2
+                        if (dt >= 0) {
+                            const int row = dt & (kHalfPts - 1), sub = dt >> 6;      // sub warp-uniform
                             const int n = h * kHalfPts + row, rl = n & 31, sl = n >> 5;
                             const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
                             const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
                             const int s = min(q * kTileSamples + sl, N - 1);
-                            float acc[28];
+                            const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
+                            const int c0 = (rid / ch) * ch;
+                            const int Bc = min(ch, P.n_rays - c0);
+                            const long long jl = (long long)(rid - c0) * N + s;
+                            const int src = c0 + ((jl < 0x7fffffffLL) ? (int)((unsigned)jl % (unsigned)Bc) : (int)(jl % Bc));
+                            const float wd[3] = {P.viewdirs[3 * src], P.viewdirs[3 * src + 1], P.viewdirs[3 * src + 2]};
+                            // thread `sub` produces K columns [16 sub, 16 sub + 16) of the 32-wide (27 used) direction encoding
+                            float acc[16];
 #pragma unroll
-                            for (int i = 0; i < 28; ++i) acc[i] = 0.f;
-                            if (sub == 0) {
-                                const float fr = P.far[rid];
-                                const float tv = P.tvals[(long long)rid * N + s];
-                                RayFast rg;
-                                ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
-                                PtsRow pr;
-                                pr.tv = tv;
-                                if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
-                                else {
-                                    for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
-                                }
-                                pts[n] = pr;
-                            } else {
-                                // direction encoding of the quirk-Q1 conditioning ray (model.py:357-360), views sub-1, sub+2, ...
-                                const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
-                                const int c0 = (rid / ch) * ch;
-                                const int Bc = min(ch, P.n_rays - c0);
-                                const long long jl = (long long)(rid - c0) * N + s;
-                                const int src = c0 + ((jl < 0x7fffffffLL) ? (int)((unsigned)jl % (unsigned)Bc) : (int)(jl % Bc));
-                                const float wd[3] = {P.viewdirs[3 * src], P.viewdirs[3 * src + 1], P.viewdirs[3 * src + 2]};
-                                for (int vv = sub - 1; vv < nv; vv += 3) {
-                                    float dc[3];
-                                    rotate_to_camera(vxs[vv], wd, dc);
+                            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                            for (int vv = 0; vv < nv; ++vv) {
+                                float dc[3];
+                                rotate_to_camera(vxs[vv], wd, dc);
 #pragma unroll
-                                    for (int i = 0; i < kDirEnc; ++i) {
-                                        float val;
-                                        if (i < 3) val = dc[i];
-                                        else {
-                                            const int q0 = i - 3;
-                                            const bool shifted = q0 >= 12;
-                                            const int qq = shifted ? q0 - 12 : q0;
-                                            const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
-                                            val = __sinf(shifted ? xb + 1.57079637f : xb);
+                                for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                                    for (int sb = 0; sb < 2; ++sb) {
+                                        const int e = sb * 16 + i;
+                                        if (sub == sb && e < kDirEnc) {
+                                            float val;
+                                            if (e < 3) val = dc[e];
+                                            else {
+                                                const int q0 = e - 3;
+                                                const bool shifted = q0 >= 12;
+                                                const int qq = shifted ? q0 - 12 : q0;
+                                                const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
+                                                val = __sinf(shifted ? xb + 1.57079637f : xb);
+                                            }
+                                            acc[i] += val;
                                         }
-                                        acc[i] += val;
                                     }
                                 }
                             }
                             const float inv = 1.0f / (float)nv;
 #pragma unroll
-                            for (int i = 0; i < 28; ++i) {
-                                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
-                                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
-                                acc[i] *= inv;
+                            for (int c2 = 0; c2 < 2; ++c2) {
+                                const int chunk = sub * 2 + c2;
+                                sts128(sbase + SM_DIR + n * 128 + ((chunk ^ (n & 7)) << 4),
+                                       make_uint4(pack_h2(acc[8 * c2] * inv, acc[8 * c2 + 1] * inv), pack_h2(acc[8 * c2 + 2] * inv, acc[8 * c2 + 3] * inv),
+                                                  pack_h2(acc[8 * c2 + 4] * inv, acc[8 * c2 + 5] * inv), pack_h2(acc[8 * c2 + 6] * inv, acc[8 * c2 + 7] * inv)));
                             }
-                            // each of the 4 threads writes one 16-byte chunk (8 of the 32 K columns, 27 used) of the DIR row
-                            float e8[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float x = 0.f;
-#pragma unroll
-                                for (int c2 = 0; c2 < 4; ++c2) { const int idx = c2 * 8 + i; if (sub == c2 && idx < 28) x = acc[idx < 28 ? idx : 0]; }
-                                e8[i] = x;
-                            }
-                            sts128(sbase + SM_DIR + n * 128 + ((sub ^ (n & 7)) << 4),
-                                   make_uint4(pack_h2(e8[0], e8[1]), pack_h2(e8[2], e8[3]), pack_h2(e8[4], e8[5]), pack_h2(e8[6], e8[7])));
                         }
-                        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));    // PTS visible to all producer threads
-                        TLAP(tp_pts);
                     }
-                    // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved) ----
+                    // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved), thread = (sub, row) ----
                     mbar_wait(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
                     TLAP(tp_encwait);
                     if (ptid < 4 * kHalfPts) {
-                        const int row = ptid >> 2, sub = ptid & 3;
+                        // sub is warp-uniform (64 consecutive threads share it): no divergence between the map / chunk variants
+                        const int row = ptid & (kHalfPts - 1), sub = ptid >> 6;
                         const PtsRow pr = pts[h * kHalfPts + row];
                         const ViewXform vx = vxs[v];
                         float ce[4], cl[3];
@@ -575,7 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             bilinear_taps(ga, gb, P.sc.plane_w, P.sc.plane_h, tp);
                         }
                         // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w)
-                        sts128(rowtab + row * 128 + sub * 32, make_uint4(tp.idx[0] * 32, tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
+                        const bool dead = (tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f);   // zeros padding
+                        sts128(rowtab + row * 128 + sub * 32, make_uint4(dead ? 0xFFFFFFFFu : (uint32_t)(tp.idx[0] * 32), tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
                         sts128(rowtab + row * 128 + sub * 32 + 16, make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
                                                                                pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
 #pragma unroll
@@ -587,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         }
                     }
                     fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
-                    mbar_arrive(BAR(ENC_READY + slot));
+                    mbar_arrive_warp(BAR(ENC_READY + slot), lane);
                     TLAP(tp_geom);
                     asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB[slot] complete
                     TLAP(tp_bar);
@@ -607,10 +627,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
                                 const uint4 off = lds128(rowtab + r * 128 + m * 32);
-                                val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
-                                val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
-                                val[m * 4 + 2] = __ldg(mapbase[m] + off.z);
-                                val[m * 4 + 3] = __ldg(mapbase[m] + off.w);
+                                if (off.x != 0xFFFFFFFFu) {          // warp-uniform: out-of-range lookups contribute exact zeros
+                                    val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
+                                    val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
+                                    val[m * 4 + 2] = __ldg(mapbase[m] + off.z);
+                                    val[m * 4 + 3] = __ldg(mapbase[m] + off.w);
+                                } else {
+                                    val[m * 4 + 0] = val[m * 4 + 1] = val[m * 4 + 2] = val[m * 4 + 3] = make_uint4(0u, 0u, 0u, 0u);
+                                }
                             }
                             __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
@@ -630,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             sts128(gdst + r * 256, make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
                                                               *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3)));
                         }
-                        mbar_arrive(BAR(G_READY + slot));
+                        mbar_arrive_warp(BAR(G_READY + slot), lane);
                         TLAP(tp_gather);
                     }
                 }
@@ -644,84 +668,99 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         // =====================================================================================
         // MMA ISSUE (one thread)
         // =====================================================================================
-        if (lane == 0) {
-            uint32_t ph_h = 0, kcount = 0;
+        {
+            // all 32 lanes run this loop (waits included); MMAs/commits are issued by one elected lane
+            uint32_t ph_h = 0, kcount = 0;      // bit b = parity of H_READY[b]
             long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0;
             TSTART();
-            const uint32_t id_trunk = idesc_f16(128, kHalfPts), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
+            const uint32_t id_blk = idesc_f16(128, 32), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
             const uint32_t dD = tmem + TM_D, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
+            // descriptor of k-step ks = base descriptor + ((ks>>2)*slab + (ks&3)*32) / 16 in the start-address field
+            auto dk = [](uint64_t base, int ks, uint32_t slab_bytes) { return base + (uint64_t)(((uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u) >> 4); };
+            auto wait_h = [&](int blk, int tag) {
+                TLAP(tm_issue);
+                mbar_wait(BAR(H_READY + blk), (ph_h >> blk) & 1u, P.err, tag); ph_h ^= 1u << blk;
+                TLAP(tm_hwait);
+                tc_fence_after();
+            };
             for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
                 for (int v = 0; v < nv; ++v) {
                     for (int h = 0; h < 2; ++h, ++kcount) {
                         const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
                         const uint32_t sENC = sbase + SM_ENC + slot * SLOT_ENC;
                         const uint32_t sHh = sH + h * (kHalfPts * 128);        // rows 64h.. of each 128-row slab
+                        uint64_t dENC[2], dHb[2];
+                        for (int bb = 0; bb < 2; ++bb) { dENC[bb] = desc_sw128(sENC + bb * 4096); dHb[bb] = desc_sw128(sHh + bb * 4096); }
                         TLAP(tm_issue);
                         mbar_wait(BAR(ENC_READY + slot), use, P.err, 10);
                         TLAP(tm_encwait);
                         tc_fence_after();
-                        // L0: D[:, 0:64] = W0enc . ENC^T
+                        // L0 of both 32-point blocks: D[:, 32b:32b+32] = W0enc . ENC[rows 32b..]^T
+                        if (elect_one()) {
+                            for (int bb = 0; bb < 2; ++bb) {
 #pragma unroll
-                        for (int ks = 0; ks < KE / 16; ++ks)
-                            mma_ts(dD, aW0 + ks * 8, desc_sw128(kaddr(sENC, ks, SLAB_ENC)), id_trunk, ks > 0);
-                        tc_commit(BAR(ACC_READY));
-                        for (int l = 1; l <= 2; ++l) {
-                            TLAP(tm_issue);
-                            mbar_wait(BAR(H_READY), ph_h, P.err, 11); ph_h ^= 1;
-                            TLAP(tm_hwait);
-                            tc_fence_after();
-                            const uint32_t aW = (l == 1) ? aW1 : aW2;
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW + ks * 8, desc_sw128(kaddr(sHh, ks, 16384)), id_trunk, ks > 0);
-                            tc_commit(BAR(ACC_READY));
+                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW0 + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
+                                tc_commit(BAR(ACC_READY + bb));
+                            }
                         }
-                        // L3: D = W3h . H^T + W3enc . ENC^T
-                        TLAP(tm_issue);
-                        mbar_wait(BAR(H_READY), ph_h, P.err, 12); ph_h ^= 1;
-                        TLAP(tm_hwait);
-                        tc_fence_after();
+                        __syncwarp();
+                        for (int l = 1; l <= 3; ++l) {
+                            const uint32_t aW = (l == 1) ? aW1 : (l == 2 ? aW2 : aW3h);
+                            for (int bb = 0; bb < 2; ++bb) {
+                                wait_h(bb, 11);                     // layer l-1 of this block is in H
+                                if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) mma_ts(dD, aW3h + ks * 8, desc_sw128(kaddr(sHh, ks, 16384)), id_trunk, ks > 0);
+                                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD + 32 * bb, aW + ks * 8, dk(dHb[bb], ks, 16384), id_blk, ks > 0);
+                                    if (l == 3) {
 #pragma unroll
-                        for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW3e + ks * 8, desc_sw128(kaddr(sENC, ks, SLAB_ENC)), id_trunk, 1);
-                        tc_commit(BAR(ACC_READY));
-                        tc_commit(BAR(ENC_FREE + slot));
-                        TLAP(tm_issue);
-                        mbar_wait(BAR(H_READY), ph_h, P.err, 13); ph_h ^= 1;      // h3 of this half written
-                        TLAP(tm_hwait);
-                        tc_fence_after();
+                                        for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, 1);
+                                    }
+                                    tc_commit(BAR(ACC_READY + bb));
+                                    if (l == 3 && bb == 1) tc_commit(BAR(ENC_FREE + slot));
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        wait_h(0, 13);                              // h3 of both blocks written
+                        wait_h(1, 13);
                     }
                     // head: Dh (+)= H3 . (Whead_h)^T      (128 points on lanes, accumulates the view mean)
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_ss(dH, desc_sw128(kaddr(sH, ks, 16384)), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
-                    if (v == nv - 1) {
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_ss(dH, desc_sw128(kaddr(sH, ks, 16384)), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
+                        if (v == nv - 1) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
-                            mma_ss(dH, desc_sw128(sDIR + ks * 32), desc_sw128(sWH + WH_DIR + ks * 32), id_head, 1);
-                        tc_commit(BAR(HEAD_READY));
-                        tc_commit(BAR(DIR_FREE));
+                            for (int ks = 0; ks < 2; ++ks)
+                                mma_ss(dH, desc_sw128(sDIR + ks * 32), desc_sw128(sWH + WH_DIR + ks * 32), id_head, 1);
+                            tc_commit(BAR(HEAD_READY));
+                            tc_commit(BAR(DIR_FREE));
+                        }
                     }
+                    __syncwarp();
                 }
-                // colour head: q -> relu -> 64x64 -> relu -> 64x3
-                mbar_wait(BAR(H_READY), ph_h, P.err, 14); ph_h ^= 1;
-                tc_fence_after();
+                // colour head: q -> relu -> 64x64 -> relu -> 64x3   (uses block-0 barriers)
+                wait_h(0, 14);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_V1 + ks * 32), id_q, ks > 0);
-                tc_commit(BAR(ACC_READY));
-                mbar_wait(BAR(H_READY), ph_h, P.err, 15); ph_h ^= 1;
-                tc_fence_after();
+                    for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_V1 + ks * 32), id_q, ks > 0);
+                    tc_commit(BAR(ACC_READY));
+                }
+                __syncwarp();
+                wait_h(0, 15);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_RGB + ks * 32), id_rgb, ks > 0);
-                tc_commit(BAR(ACC_READY));
+                    for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_RGB + ks * 32), id_rgb, ks > 0);
+                    tc_commit(BAR(ACC_READY));
+                }
+                __syncwarp();
                 // accumulator drained by the colour epilogue before the next tile overwrites it
-                mbar_wait(BAR(H_READY), ph_h, P.err, 16); ph_h ^= 1;
-                tc_fence_after();
+                wait_h(0, 16);
             }
-            if (P.dbg) {
+            if (P.dbg && lane == 0) {
                 long long* d = P.dbg + (size_t)blockIdx.x * 16;
                 d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue;
             }
@@ -732,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         // =====================================================================================
         const int c = warp * 32 + lane;                 // neuron (trunk) / point row (head)
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ph_acc = 0, ph_head = 0, kcount = 0;
+        uint32_t ph_acc = 0, ph_head = 0, kcount = 0;     // bit b = parity of ACC_READY[b]
         long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
         TSTART();
         uint32_t hoff[8];
@@ -748,33 +787,33 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
                         const float bias = lds_f32(sBias + 4 * (l * 128 + c));
-                        TLAP(te_work);
-                        mbar_wait(BAR(ACC_READY), ph_acc, P.err, 20 + l); ph_acc ^= 1;
-                        TLAP(te_accwait);
-                        tc_fence_after();
-                        uint32_t gsrc = 0;
-                        if (l == 0) { mbar_wait(BAR(G_READY + slot), use, P.err, 24); gsrc = sbase + SM_G0 + slot * SLOT_G + c * 2; TLAP(te_gwait); }
-                        if (l == 3) gsrc = sbase + SM_G3 + slot * SLOT_G + c * 2;
-                        const __half* gp = reinterpret_cast<const __half*>(sgen + (gsrc - sbase));      // G[slot][0][c]
-                        unsigned char* hp = sgen + (sHh - sbase);
+                        const bool hasG = (l == 0) | (l == 3);
+                        const __half* gbase = reinterpret_cast<const __half*>(sgen + (l == 0 ? SM_G0 : SM_G3) + slot * SLOT_G) + c;   // G[slot][0][c]
 #pragma unroll 1
-                        for (int cb = 0; cb < kHalfPts / 8; ++cb) {
-                            float gv[8];
+                        for (int bb = 0; bb < 2; ++bb) {
+                            if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); TLAP(te_gwait); }
+                            // gathered features of this block first (plain shared loads, all in flight), then the accumulator
+                            float gv[32];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) gv[i] = gsrc ? __half2float(gp[(cb * 8 + i) * 128]) : 0.f;
-                            uint32_t r[8];
-                            tmem_ld8(lane_base + TM_D + cb * 8, r);
+                            for (int i = 0; i < 32; ++i) gv[i] = hasG ? __half2float(gbase[(bb * 32 + i) * 128]) : 0.f;
+                            TLAP(te_work);
+                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
+                            TLAP(te_accwait);
+                            tc_fence_after();
+                            uint32_t r[32];
+                            tmem_ld32(lane_base + TM_D + bb * 32, r);
                             tc_wait_ld();
+                            unsigned char* hp = sgen + (sHh - sbase) + bb * 32 * 128;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
+                            for (int i = 0; i < 32; ++i) {
                                 const float x = fmaxf(__uint_as_float(r[i]) + bias + gv[i], 0.f);
-                                *reinterpret_cast<__half*>(hp + (cb * 8 + i) * 128 + hoff[i]) = __float2half_rn(x);
+                                *reinterpret_cast<__half*>(hp + i * 128 + hoff[i & 7]) = __float2half_rn(x);
                             }
+                            if (l == 3 && bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
+                            tc_fence_before();
+                            fence_proxy_async();
+                            mbar_arrive_warp(BAR(H_READY + bb), lane);
                         }
-                        if (l == 3) mbar_arrive(BAR(G_FREE + slot));
-                        tc_fence_before();
-                        fence_proxy_async();
-                        mbar_arrive(BAR(H_READY));
                     }
                 }
             }
@@ -804,8 +843,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                            make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
                 }
             }
-            tc_fence_before(); fence_proxy_async(); mbar_arrive(BAR(H_READY));
-            mbar_wait(BAR(ACC_READY), ph_acc, P.err, 27); ph_acc ^= 1;
+            tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(H_READY), lane);
+            mbar_wait(BAR(ACC_READY), ph_acc & 1u, P.err, 27); ph_acc ^= 1u;
             tc_fence_after();
             {
                 uint32_t r[64];
@@ -821,8 +860,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                            make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
                 }
             }
-            tc_fence_before(); fence_proxy_async(); mbar_arrive(BAR(H_READY));
-            mbar_wait(BAR(ACC_READY), ph_acc, P.err, 28); ph_acc ^= 1;
+            tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(H_READY), lane);
+            mbar_wait(BAR(ACC_READY), ph_acc & 1u, P.err, 28); ph_acc ^= 1u;
             tc_fence_after();
             {
                 uint32_t r[16];
@@ -836,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     }
                 }
             }
-            tc_fence_before(); mbar_arrive(BAR(H_READY));
+            tc_fence_before(); mbar_arrive_warp(BAR(H_READY), lane);
             TLAP(te_head);
         }
         if (P.dbg && threadIdx.x == 0) {
