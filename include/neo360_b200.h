@@ -177,6 +177,39 @@ int neo_index_local(const NeoScene* scene, const float* pts, int M, float* out, 
 int neo_field_eval(const NeoScene* scene, const NeoRays* rays, const float* far, const float* t_vals, int N,
                    int mlp_index, int precision, float* rgb, float* sigma, void* stream);
 
+/* ---- vanilla two-level NeRF: models/vanilla_nerf/model.py:44-216 ---- */
+typedef struct {
+    const float* w[8];        /* pts_linears.{0..7}.weight: (256,63) (256,256)x4 (256,319) (256,256)x2 */
+    const float* b[8];
+    const float *wb, *bb;     /* bottleneck_layer (256,256) */
+    const float *wsig, *bsig; /* density_layer (1,256) */
+    const float *wv0, *bv0;   /* views_linear.0 (128, 256+27) */
+    const float *wrgb, *brgb; /* rgb_layer (3,128) */
+} NeoVanillaMLPParams;
+typedef struct NeoVanilla NeoVanilla;
+typedef struct {
+    int n_coarse, n_fine, white_bkgd;
+    float near_plane, far_plane;   /* the scalar near / far the caller passes to NeRF.forward (model.py:154) */
+    const float* u0;               /* randomized: (n_rays, n_coarse+1) uniforms, helper.py:438; NULL = deterministic */
+    const float* u1;               /* randomized: (n_rays, n_fine) uniforms, helper.py:587 */
+} NeoVanillaCfg;
+typedef struct {
+    float* comp_rgb[2];  /* (n_rays,3)   model.py:214 returns (comp_rgb, acc, depth) per level */
+    float* acc[2];       /* (n_rays) */
+    float* depth[2];     /* (n_rays) */
+    float* t[2];         /* optional debug taps: (n_rays,N_l) */
+    float* sigma[2];
+    float* rgb_s[2];     /* (n_rays,N_l,3) */
+    float* weights[2];
+} NeoVanillaOut;
+/* mlps[2] = {coarse_mlp, fine_mlp} */
+int neo_vanilla_create(const NeoVanillaMLPParams mlps[2], NeoVanilla** out, void* stream);
+void neo_vanilla_free(NeoVanilla* v);
+size_t neo_vanilla_workspace_bytes(int n_rays, const NeoVanillaCfg* cfg);
+/* NeRF.forward (models/vanilla_nerf/model.py:154-216); rays->chunk is ignored (no cross-ray coupling in this model) */
+int neo_vanilla_render_fwd(const NeoVanilla* v, const NeoRays* rays, const NeoVanillaCfg* cfg, NeoVanillaOut* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* bench support: CUDA events around every field-kernel launch on the launching stream + launch accounting.
  * neo_profile(1) resets and enables, neo_profile(0) resets and disables; neo_profile_read synchronises. */
 int neo_profile(int enable);

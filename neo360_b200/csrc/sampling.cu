@@ -303,11 +303,13 @@ __global__ void composite_kernel(const float* __restrict__ rgb, const float* __r
     const float* tb = t + (long long)b * N;
     const float* sb = sigma + (long long)b * N;
     const float* cb = rgb + (long long)b * N * 3;
+    // in_sphere: 1 = NeO-360 fg (last interval far - t_N, |d| scale), 0 = NeO-360 bg (descending s, last 1e10),
+    //            2 = vanilla NeRF (ascending t, last 1e10, |d| scale, depth nan_to_num)   vanilla_nerf/helper.py:521-559
     float dn = 1.f, fr = 0.f;
     if (in_sphere) {
         const float* dd = d + 3 * b;
         dn = __fsqrt_rn(dot3_(dd, dd));
-        fr = far[b];
+        if (in_sphere == 1) fr = far[b];
     }
     float carry = 1.f;      // T of everything before this 32-sample block
     float acc = 0.f, r = 0.f, gch = 0.f, bch = 0.f, dep = 0.f;
@@ -316,9 +318,11 @@ __global__ void composite_kernel(const float* __restrict__ rgb, const float* __r
         bool ok = k < N;
         float tk = ok ? tb[k] : 0.f;
         float dist;
-        if (in_sphere) {
+        if (in_sphere == 1) {
             float nxt = (k + 1 < N) ? tb[min(k + 1, N - 1)] : fr;
             dist = mul_(sub_(nxt, tk), dn);
+        } else if (in_sphere == 2) {
+            dist = mul_((k + 1 < N) ? sub_(tb[min(k + 1, N - 1)], tk) : 1e10f, dn);
         } else {
             dist = (k + 1 < N) ? sub_(tk, tb[min(k + 1, N - 1)]) : 1e10f;
         }
@@ -350,6 +354,7 @@ __global__ void composite_kernel(const float* __restrict__ rgb, const float* __r
         if (comp) { comp[b * 3 + 0] = r; comp[b * 3 + 1] = gch; comp[b * 3 + 2] = bch; }
         if (acc_out) acc_out[b] = acc;
         if (lam_out) lam_out[b] = carry;     // T[..., -1]
+        if (in_sphere == 2 && dep != dep) dep = INFINITY;      // torch.nan_to_num(depth, inf), quirk Q10
         if (depth_out) depth_out[b] = dep;
     }
 }

@@ -107,3 +107,25 @@ def target_pose(view: int = 0, n_views: int = 100) -> Tensor:
     """Turntable target camera `view` of `n_views` (radius 0.6-0.9, height 0.2-0.4, inside the unit sphere)."""
     f = view / max(n_views, 1)
     return look_at_pose(360.0 * f + 47.0, 0.3 + 0.1 * math.sin(2 * math.pi * f), 0.75 + 0.15 * math.cos(2 * math.pi * f))
+
+
+VANILLA_PREFIXES = ("coarse_mlp.", "fine_mlp.")
+
+
+def make_vanilla_params(seed: int = 0, density_bias_shift: float = 1.0) -> Dict[str, Tensor]:
+    """Two NeRFMLP parameter sets with the reference's shapes (models/vanilla_nerf/model.py:44-98): pts_linears.0 (256,63),
+    .1-.4/.6/.7 (256,256), .5 (256,319), views_linear.0 (128,283), bottleneck (256,256), density (1,256), rgb (3,128)."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    P: Dict[str, Tensor] = {}
+    for pre in VANILLA_PREFIXES:
+        shapes = {f"pts_linears.{i}": (256, 63 if i == 0 else (319 if i == 5 else 256)) for i in range(8)}
+        shapes.update({"views_linear.0": (128, 283), "bottleneck_layer": (256, 256), "density_layer": (1, 256), "rgb_layer": (3, 128)})
+        for name, (o, i) in shapes.items():
+            w, b = _linear(o, i, g, xavier=(name != "views_linear.0"))
+            gain = {"density_layer": 3.0, "rgb_layer": 4.0, "views_linear.0": 2.0}.get(name, 1.3)
+            w = w * gain
+            if name == "density_layer":
+                b = b + density_bias_shift
+            P[pre + name + ".weight"] = w
+            P[pre + name + ".bias"] = b
+    return P

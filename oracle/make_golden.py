@@ -195,6 +195,50 @@ def e2e(ns, out, tag, img_wh, plane_hw, B, nc, nf, seed):
         out[f"{tag}_u_{k}"] = v
 
 
+def vanilla(ns, path):
+    """Golden vectors for the vanilla-NeRF renderer (row a17) from the unmodified reference NeRF module."""
+    from oracle import vanilla_oracle as vor
+    out = {}
+    for tag, (W, H, B, nc, nf, seed) in {"v_tiny": (64, 48, 96, 16, 8, 0), "v_cfg1": (64, 64, 1024, 64, 64, 1)}.items():
+        P = synth.make_vanilla_params(seed)
+        torch.manual_seed(seed)
+        net = ns.van_model.NeRF(num_coarse_samples=nc, num_fine_samples=nf).eval()
+        missing, unexpected = net.load_state_dict(P, strict=True)
+        pose = synth.target_pose(5, 100)
+        dirs = ns.ray_utils.get_ray_directions(H, W, 0.8 * W)
+        ro, vd, rd = ns.ray_utils.get_rays(dirs, pose[:3, :4], output_view_dirs=True)
+        g = torch.Generator().manual_seed(50 + seed)
+        sel = torch.randperm(H * W, generator=g)[:B]
+        # the dataset hands un-normalised rays_d to the vanilla model (datasets/nerds360.py); exercise |rays_d| != 1 (quirk Q15)
+        scale = 0.5 + torch.rand(B, 1, generator=g)
+        rays = {"rays_o": ro[sel].contiguous(), "rays_d": (rd[sel] * scale).contiguous(), "viewdirs": vd[sel].contiguous()}
+        near, far = 0.2, 3.0
+        with torch.no_grad():
+            ev = net(rays, False, True, near, far)
+            rnd = {"u0": torch.rand(B, nc + 1, generator=g), "u1": torch.rand(B, nf, generator=g)}
+            with RandQueue([rnd["u0"], rnd["u1"]]):
+                rr = net(rays, True, False, near, far)
+            o_ev, aux = vor.render(rays, P, nc, nf, near, far, True, return_aux=True)
+            o_rr = vor.render(rays, P, nc, nf, near, far, False, rand=rnd)
+        worst = 0.0
+        for got, ref in ((o_ev, ev), (o_rr, rr)):
+            for lvl in range(2):
+                for a, b in zip(got[lvl], ref[lvl]):
+                    worst = max(worst, maxdiff(a, b))
+        assert worst < 2e-4, worst
+        print(f"vanilla[{tag}]: oracle vs reference max|diff| = {worst:.3e}")
+        out.update({f"{tag}_cfg": np.array([W, H, B, nc, nf, seed]), f"{tag}_rays_o": rays["rays_o"], f"{tag}_rays_d": rays["rays_d"],
+                    f"{tag}_viewdirs": rays["viewdirs"], f"{tag}_u0": rnd["u0"], f"{tag}_u1": rnd["u1"]})
+        for lvl in range(2):
+            for n_, a, b in zip(("rgb", "acc", "depth"), ev[lvl], rr[lvl]):
+                out[f"{tag}_eval{lvl}_{n_}"] = a
+                out[f"{tag}_rand{lvl}_{n_}"] = b
+            for k in ("t", "sigma", "rgb"):
+                out[f"{tag}_aux{lvl}_{k}"] = aux[lvl][k] if tag == "v_tiny" else aux[lvl][k][:32]
+    np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     ns = ref_shim.load()
     torch.set_grad_enabled(False)
@@ -207,6 +251,7 @@ def main():
     path = os.path.join(GOLD, "neo360_reference_vectors.npz")
     np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
     print("wrote", path, os.path.getsize(path), "bytes")
+    vanilla(ns, os.path.join(GOLD, "vanilla_reference_vectors.npz"))
 
 
 if __name__ == "__main__":

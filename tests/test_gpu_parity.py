@@ -300,3 +300,34 @@ def test_end_to_end_tc_vs_reference_vectors(cuda, golden, tag):
         for n_, v in zip(EV, ev[lvl]):
             assert md(v, T(g[f"{tag}_eval{lvl}_{n_}"])) < 3e-2, (lvl, n_)
     assert orc.psnr(ev[1][0].cpu(), T(g[f"{tag}_eval1_comp_rgb"])) > 40
+
+
+# ---------------- vanilla NeRF (row a17) ----------------
+
+@pytest.mark.parametrize("tag", ["v_tiny", "v_cfg1"])
+def test_vanilla_nerf_vs_reference_vectors(cuda, tag):
+    """CUDA vanilla NeRF (fp32, reference formulation) against outputs of the UNMODIFIED reference NeRF module.
+    v_cfg1 = BASELINE configs[0] (1024 rays, 64+64 samples).  Tolerance: >=99% of outputs within 2e-4, L-inf 5e-3."""
+    import os
+    from neo360_b200.vanilla import NeRF
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vanilla_reference_vectors.npz"))
+    W, H, B, nc, nf, seed = [int(x) for x in g[f"{tag}_cfg"]]
+    net = NeRF(num_coarse_samples=nc, num_fine_samples=nf).eval()
+    net.load_state_dict(synth.make_vanilla_params(seed))
+    net = net.to(cuda)
+    rays = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs")}
+    with torch.no_grad():
+        ev = net(rays, False, True, 0.2, 3.0, debug=True)
+        dbg = net.last_debug
+        rays_r = dict(rays)
+        rays_r["_uniforms"] = [T(g[f"{tag}_u0"]).to(cuda), T(g[f"{tag}_u1"]).to(cuda)]
+        rr = net(rays_r, True, False, 0.2, 3.0)
+    torch.cuda.synchronize()
+    if tag == "v_tiny":      # stratified positions are bit-exact
+        assert md(dbg["t"][0], T(g["v_tiny_aux0_t"])) == 0
+        assert md(dbg["sigma"][0], T(g["v_tiny_aux0_sigma"])) < 1e-4 and md(dbg["rgb_s"][0], T(g["v_tiny_aux0_rgb"])) < 1e-4
+    for lvl in range(2):
+        for n_, a, b in zip(("rgb", "acc", "depth"), ev[lvl], rr[lvl]):
+            for got, ref in ((a, g[f"{tag}_eval{lvl}_{n_}"]), (b, g[f"{tag}_rand{lvl}_{n_}"])):
+                diff = (got.cpu().double() - T(ref).double()).abs()
+                assert float(diff.max()) < 5e-3 and float((diff > 2e-4).double().mean()) <= 0.01, (lvl, n_, float(diff.max()))

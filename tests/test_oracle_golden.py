@@ -92,3 +92,28 @@ def test_chunked_render_matches_single_chunk(golden):
         a = orc.render_chunked(rays, osc, P, nc, nf, chunk=rays["rays_o"].shape[0])
     assert md(a["comp_rgb"], golden["tiny_eval1_comp_rgb"]) < 5e-4
     assert md(a["depth"], golden["tiny_eval1_depth"]) < 5e-4
+
+
+# ---------------- vanilla NeRF (row a17; BASELINE configs[0] is the CPU-runnable plumbing case) ----------------
+
+@pytest.fixture(scope="module")
+def vgolden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vanilla_reference_vectors.npz"))
+
+
+@pytest.mark.parametrize("tag", ["v_tiny", "v_cfg1"])
+def test_vanilla_oracle_vs_reference_vectors(vgolden, tag):
+    """v_cfg1 = BASELINE configs[0]: 64x64 crop, 1024 rays, 64+64 samples, on CPU."""
+    from oracle import vanilla_oracle as vor
+    g = vgolden
+    W, H, B, nc, nf, seed = [int(x) for x in g[f"{tag}_cfg"]]
+    P = synth.make_vanilla_params(seed)
+    rays = {k: T(g[f"{tag}_{k}"]) for k in ("rays_o", "rays_d", "viewdirs")}
+    with torch.no_grad():
+        ev = vor.render(rays, P, nc, nf, 0.2, 3.0, True)
+        rr = vor.render(rays, P, nc, nf, 0.2, 3.0, False, rand={"u0": T(g[f"{tag}_u0"]), "u1": T(g[f"{tag}_u1"])})
+    for lvl in range(2):
+        for n_, a, b in zip(("rgb", "acc", "depth"), ev[lvl], rr[lvl]):
+            assert md(a, g[f"{tag}_eval{lvl}_{n_}"]) < 1e-5, (lvl, n_)
+            assert md(b, g[f"{tag}_rand{lvl}_{n_}"]) < 1e-5, (lvl, n_)
