@@ -248,13 +248,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    wh = (IMG_W, IMG_H) if (n == IMG_W * IMG_H and not os.environ.get("NEO360_NO_BLOCK_ORDER")) else None
+
     def step_resident(s):
-        return net.render_rays_test(devrays[s % len(devrays)], chunk=CHUNK)
+        return net.render_rays_test(devrays[s % len(devrays)], chunk=CHUNK, img_wh=wh)
 
     def step_e2e(s):
         o, d = host[s % len(host)]
         do, dd = o.to(dev, non_blocking=True), d.to(dev, non_blocking=True)
-        r = net.render_rays_test({"rays_o": do, "rays_d": dd, "viewdirs": dd}, chunk=CHUNK)
+        r = net.render_rays_test({"rays_o": do, "rays_d": dd, "viewdirs": dd}, chunk=CHUNK, img_wh=wh)
         out_host[:, :3].copy_(r["rgb"], non_blocking=True)
         out_host[:, 3].copy_(r["depth"], non_blocking=True)
         return r

@@ -95,6 +95,8 @@ typedef struct {
     const float* rays_o;     /* (n_rays,3) */
     const float* rays_d;     /* (n_rays,3) */
     const float* viewdirs;   /* (n_rays,3) */
+    const int* ray_order;    /* optional (n_rays) permutation used only for locality: the TC kernel's g-th tile covers rays
+                                ray_order[32g..32g+31] (e.g. 8x4 pixel blocks of a frame); results are unchanged.  NULL = identity */
 } NeoRays;
 
 typedef struct {

@@ -29,7 +29,7 @@ class NeoSceneDesc(C.Structure):
 
 class NeoRays(C.Structure):
     _fields_ = [("n_rays", C.c_int), ("chunk", C.c_int), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p),
-                ("viewdirs", C.c_void_p)]
+                ("viewdirs", C.c_void_p), ("ray_order", C.c_void_p)]
 
 
 class NeoCfg(C.Structure):

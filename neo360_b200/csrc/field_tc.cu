@@ -1028,7 +1028,7 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
     }
     Params P;
     P.rays_o = rays->rays_o; P.rays_d = rays->rays_d; P.viewdirs = rays->viewdirs; P.far = far; P.tvals = t;
-    P.ray_order = nullptr;
+    P.ray_order = rays->ray_order;
     P.n_rays = rays->n_rays; P.N = N; P.chunk = rays->chunk; P.nv = sc->dev.nv;
     P.sg = (N + kTileSamples - 1) / kTileSamples;
     const long long groups = ((long long)rays->n_rays + kTileRays - 1) / kTileRays;

@@ -193,6 +193,10 @@ class NeRF_TP(nn.Module):
         r.n_rays = n
         r.chunk = int(chunk if chunk is not None else (self.chunk or 0))
         r.rays_o, r.rays_d, r.viewdirs = L.ptr(o), L.ptr(d), L.ptr(vd)
+        order = rays.get("_ray_order")
+        if order is not None:
+            keep.append(order)
+            r.ray_order = order.data_ptr()
         need = lib.neo_render_workspace_bytes(n, C.byref(cfg))
         if need == 0:
             raise RuntimeError("neo360_b200: " + lib.neo_last_error().decode())
@@ -269,9 +273,26 @@ class NeRF_TP(nn.Module):
         """Synchronise and surface deferred device-side errors (the reference's asserts, helper.py:271,426)."""
         L.check(L.load().neo_check_async(self._scene.handle, torch.cuda.current_stream().cuda_stream))
 
+    def _blocked_order(self, n: int, img_wh, dev) -> torch.Tensor:
+        """Permutation visiting a row-major W x H frame in 8x4 pixel blocks: the 32 rays of a TC tile then hit neighbouring
+        texels at every sample (L1 locality).  Pure scheduling: every ray's result is unchanged."""
+        key = (n, int(img_wh[0]), int(img_wh[1]), str(dev))
+        if getattr(self, "_order_key", None) != key:
+            W = int(img_wh[0])
+            idx = torch.arange(n, device=dev)
+            y, x = idx // W, idx % W
+            k = ((y // 4) * ((W + 7) // 8) + x // 8) * 32 + (y % 4) * 8 + (x % 8)
+            self._order = torch.argsort(k).to(torch.int32).contiguous()
+            self._order_key = key
+        return self._order
+
     @torch.no_grad()
-    def render_rays_test(self, batch: Dict[str, torch.Tensor], chunk: int = 1024, white_bkgd: bool = False):
+    def render_rays_test(self, batch: Dict[str, torch.Tensor], chunk: int = 1024, white_bkgd: bool = False, img_wh=None):
         """models/neo360/model.py:861-907 without the Python chunk loop: one call over every ray of the frame; the
-        reference's per-chunk view-direction conditioning (quirk Q1) is reproduced from `chunk`."""
+        reference's per-chunk view-direction conditioning (quirk Q1) is reproduced from `chunk`.  `img_wh=(W,H)` (rays are the
+        row-major pixels of a frame) lets the kernel walk the frame in 8x4 pixel blocks."""
+        if img_wh is not None and batch["rays_o"].shape[0] == int(img_wh[0]) * int(img_wh[1]):
+            batch = dict(batch)
+            batch["_ray_order"] = self._blocked_order(batch["rays_o"].shape[0], img_wh, batch["rays_o"].device)
         out = self.forward(batch, False, white_bkgd, None, None, out_depth=True, chunk=chunk)[1]
         return {"rgb": out[0], "fg_rgb": out[1], "bg_rgb": out[2], "depth": out[5], "fg_acc": out[3]}

@@ -240,6 +240,11 @@ def test_chunked_frame_matches_oracle_chunk_loop(cuda):
         diff = (got[k].cpu() - ref[rk]).abs()
         assert float(diff.max()) < 5e-3 and float((diff > 2e-4).float().mean()) < 0.01, (k, float(diff.max()))
     assert orc.psnr(got["rgb"].cpu(), ref["comp_rgb"]) > 60
+    # walking the frame in 8x4 pixel blocks is pure scheduling: bit-identical output
+    with torch.no_grad():
+        blk = net.render_rays_test({k: v.to(cuda) for k, v in rays.items()}, chunk=512, img_wh=(W, H))
+    for k in ("rgb", "depth"):
+        assert md(blk[k], got[k]) == 0
     # sanity: ignoring the chunk size gives a measurably different image (the quirk is real and reproduced)
     assert float((wrong["rgb"].cpu() - ref["comp_rgb"]).abs().max()) > 1e-3
 
@@ -331,3 +336,18 @@ def test_vanilla_nerf_vs_reference_vectors(cuda, tag):
             for got, ref in ((a, g[f"{tag}_eval{lvl}_{n_}"]), (b, g[f"{tag}_rand{lvl}_{n_}"])):
                 diff = (got.cpu().double() - T(ref).double()).abs()
                 assert float(diff.max()) < 5e-3 and float((diff > 2e-4).double().mean()) <= 0.01, (lvl, n_, float(diff.max()))
+
+
+def test_tc_blocked_frame_order_is_pure_scheduling(cuda):
+    """NEO_PREC_TC with NeoRays.ray_order (8x4 pixel blocks) must give bit-identical pixels to the identity order."""
+    W, H, nc, nf = 48, 36, 24, 12
+    net, osc, P = make_net(cuda, (W, H), (24, 32), nc, nf, 2, precisions=("tc",), precision="tc")
+    pose = synth.target_pose(11, 100)
+    ro, vd, rd, _ = orc.rays_from_pose(orc.ray_directions(H, W, 0.8 * W), pose[:3, :4])
+    rays = {"rays_o": ro.to(cuda), "rays_d": rd.to(cuda), "viewdirs": vd.to(cuda)}
+    with torch.no_grad():
+        a = net.render_rays_test(rays, chunk=512)
+        b = net.render_rays_test(rays, chunk=512, img_wh=(W, H))
+    net.check()
+    for k in ("rgb", "fg_rgb", "bg_rgb", "depth"):
+        assert md(a[k], b[k]) == 0, k
