@@ -218,9 +218,11 @@ int neo_profile(int enable);
 int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches, double* points);
 
 /* Self-test of the tcgen05 building blocks of the NEO_PREC_TC path (TMEM-resident A operand, 128B-swizzled K-major
- * operand tiles, TMEM loads): X (128,128), W (128,128), Wn (80,128) fp32 device -> out1 (128,128) = W X^T,
- * out2 (128,80) = X Wn^T, computed with fp16 operands / fp32 accumulation. */
-int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, void* stream);
+ * operand tiles in K-major and MN-major form, TMEM loads): X (128,128), W (128,128), Wn (80,128) fp32 device ->
+ * out1 = out3 (128,128) = W X^T (B operand K-major / MN-major), out2 = out4 (128,80) = X Wn^T (A operand K-major / MN-major),
+ * computed with fp16 operands / fp32 accumulation. */
+int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, float* out3, float* out4,
+                    void* stream);
 
 /* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 16)
  * int64; NULL disables.  Roles and slots are documented in csrc/field_tc.cu. */

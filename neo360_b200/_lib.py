@@ -84,7 +84,7 @@ SYMBOLS = {
     "neo_vanilla_render_fwd": (C.c_int, [C.c_void_p, C.POINTER(NeoRays), C.POINTER(NeoVanillaCfg), C.POINTER(NeoVanillaOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "neo_profile": (C.c_int, [C.c_int]),
     "neo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
-    "neo_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "neo_tc_selftest": (C.c_int, [C.c_void_p] * 8),
     "neo_tc_debug": (C.c_int, [C.c_void_p]),
     "neo_last_error": (C.c_char_p, []),
     "neo_version": (C.c_char_p, []),

@@ -106,21 +106,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // %3: suspend-time hint (ns); wakes on completion
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {      // ~2 s
+        if (++spins > (1u << 26)) {                 // each failed try_wait suspends the warp for a while: >> 1 s in total
             if (err) atomicExch(err, 1000 + tag);
             __trap();
         }
     }
+}
+// Group wait: ONE warp polls the mbarrier, the rest of the group blocks on a hardware named barrier (no polling instructions:
+// a dozen warps spinning on try_wait were eating ~40 % of the SM's issue slots).  bar.sync orders memory for the whole group.
+__device__ __forceinline__ void group_wait(uint32_t bar, uint32_t parity, bool poller, int bar_id, int nthreads, int* err, int tag) {
+    if (poller) mbar_wait(bar, parity, err, tag);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
 }
 // one lane of a fully converged warp (the MMA warp keeps warp-uniform control flow so descriptors stay in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -154,9 +160,25 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
+// MN-major, 128-byte-swizzled operand: 64 consecutive M/N elements (128 B) per K row, 8 K rows per 1024-B atom;
+// SBO = byte stride between 8-K-row atoms, LBO = byte stride between 64-element groups along M/N.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// byte offset of element (mn, k) in an MN-major SW128 tile of 64 M/N elements (atoms of 8 K rows, contiguous)
+__host__ __device__ inline uint32_t mn128_off(int mn, int k) {
+    return (uint32_t)((k >> 3) * 1024 + (k & 7) * 128 + ((((mn & 63) >> 3) ^ (k & 7)) << 4) + (mn & 7) * 2);
+}
 // kind::f16 instruction descriptor: fp16 A/B, fp32 accumulate, K-major A and B
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T     (A: M x 16 from TMEM, B: N x 16 K-major from smem)
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
@@ -624,31 +646,33 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll 1
                         for (int r = pw; r < kHalfPts; r += kProducerWarps) {
                             uint4 val[16];
+                            bool live[4];
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
                                 const uint4 off = lds128(rowtab + r * 128 + m * 32);
-                                if (off.x != 0xFFFFFFFFu) {          // warp-uniform: out-of-range lookups contribute exact zeros
+                                live[m] = off.x != 0xFFFFFFFFu;         // warp-uniform: out-of-range lookups contribute exact zeros
+                                if (live[m]) {
                                     val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
                                     val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
                                     val[m * 4 + 2] = __ldg(mapbase[m] + off.z);
                                     val[m * 4 + 3] = __ldg(mapbase[m] + off.w);
-                                } else {
-                                    val[m * 4 + 0] = val[m * 4 + 1] = val[m * 4 + 2] = val[m * 4 + 3] = make_uint4(0u, 0u, 0u, 0u);
                                 }
                             }
                             __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
-                                const uint4 wq = lds128(rowtab + r * 128 + m * 32 + 16);
-                                const uint32_t wv[4] = {wq.x, wq.y, wq.z, wq.w};
+                                if (live[m]) {
+                                    const uint4 wq = lds128(rowtab + r * 128 + m * 32 + 16);
+                                    const uint32_t wv[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const __half2 w = *reinterpret_cast<const __half2*>(&wv[k]);
-                                    const uint4& x = val[m * 4 + k];
-                                    a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.x), a0);
-                                    a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.y), a1);
-                                    a2 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.z), a2);
-                                    a3 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.w), a3);
+                                    for (int k = 0; k < 4; ++k) {
+                                        const __half2 w = *reinterpret_cast<const __half2*>(&wv[k]);
+                                        const uint4& x = val[m * 4 + k];
+                                        a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.x), a0);
+                                        a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.y), a1);
+                                        a2 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.z), a2);
+                                        a3 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.w), a3);
+                                    }
                                 }
                             }
                             sts128(gdst + r * 256, make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
@@ -896,18 +920,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                           const float* __restrict__ Wn, float* __restrict__ out1,
-                                                          float* __restrict__ out2, int* err) {
+                                                          float* __restrict__ out2, float* __restrict__ out3,
+                                                          float* __restrict__ out4, int* err) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t sX = sbase, sWn = sbase + 32768, bar = sbase + 32768 + 20480;
-    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + 32768 + 20480 + 8);
+    const uint32_t sX = sbase, sWn = sbase + 32768, sXmn = sbase + 53248, bar = sbase + 86016;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + 86016 + 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) tmem_alloc(sbase + 32768 + 20480 + 8, 512);
+    if (warp == 0) tmem_alloc(sbase + 86016 + 16, 512);
     __half* xs = reinterpret_cast<__half*>(sgen);
     __half* ws = reinterpret_cast<__half*>(sgen + 32768);
+    __half* xm = reinterpret_cast<__half*>(sgen + 53248);       // X again, MN-major: two 64-point tiles of 16 KB
     for (int e = threadIdx.x; e < 128 * 128; e += 128) xs[sw128_off(e / 128, e % 128, 128) / 2] = __float2half_rn(X[e]);
+    for (int e = threadIdx.x; e < 128 * 128; e += 128) {
+        const int n = e / 128, k = e % 128;
+        xm[((n >> 6) * 16384 + mn128_off(n, k)) / 2] = __float2half_rn(X[e]);
+    }
     for (int e = threadIdx.x; e < 80 * 128; e += 128) ws[sw128_off(e / 128, e % 128, 80) / 2] = __float2half_rn(Wn[e]);
     fence_proxy_async();
     tc_fence_before();
@@ -931,6 +961,11 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
         for (int ks = 0; ks < 8; ++ks)
             mma_ss(tmem + 128, desc_sw128(sX + (ks >> 2) * 16384 + (ks & 3) * 32), desc_sw128(sWn + (ks >> 2) * 10240 + (ks & 3) * 32),
                    idesc_f16(128, 80), ks > 0);
+        // MN-major B operand, four N=32 blocks (two per 64-point tile): out3 = W X^T again, columns 256..383 hold W so use D at 384
+        for (int blk = 0; blk < 4; ++blk)
+            for (int ks = 0; ks < 8; ++ks)
+                mma_ts(tmem + 384 + 32 * blk, tmem + 256 + ks * 8,
+                       desc_mn_sw128(sXmn + (blk >> 1) * 16384 + (blk & 1) * 64 + ks * 2048, 16384, 1024), idesc_f16(128, 32, 0, 1), ks > 0);
         tc_commit(bar);
     }
     mbar_wait(bar, 0, err, 99);
@@ -940,12 +975,33 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
         tmem_ld32(lane_base + cb * 32, r);
         tc_wait_ld();
         for (int i = 0; i < 32; ++i) out1[c * 128 + cb * 32 + i] = __uint_as_float(r[i]);
+        tmem_ld32(lane_base + 384 + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) out3[c * 128 + cb * 32 + i] = __uint_as_float(r[i]);
     }
     for (int j = 0; j < 5; ++j) {
         uint32_t r[16];
         tmem_ld16(lane_base + 128 + 16 * j, r);
         tc_wait_ld();
         for (int i = 0; i < 16; ++i) out2[c * 80 + 16 * j + i] = __uint_as_float(r[i]);
+    }
+    // MN-major A operand (M = 128 points = two 64-groups, LBO 16 KB): out4 = X Wn^T again, into columns 128..207
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        for (int ks = 0; ks < 8; ++ks)
+            mma_ss(tmem + 128, desc_mn_sw128(sXmn + ks * 2048, 16384, 1024), desc_sw128(sWn + (ks >> 2) * 10240 + (ks & 3) * 32),
+                   idesc_f16(128, 80, 1, 0), ks > 0);
+        tc_commit(bar);
+    }
+    mbar_wait(bar, 1, err, 98);
+    tc_fence_after();
+    for (int j = 0; j < 5; ++j) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + 128 + 16 * j, r);
+        tc_wait_ld();
+        for (int i = 0; i < 16; ++i) out4[c * 80 + 16 * j + i] = __uint_as_float(r[i]);
     }
     tc_fence_before();
     __syncthreads();
@@ -1055,12 +1111,14 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
 
 }  // namespace neo
 
-// X (128,128) W (128,128) Wn (80,128) device fp32 -> out1 (128,128) = W X^T, out2 (128,80) = X Wn^T, fp16 operands
-extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, void* stream) {
+// X (128,128) W (128,128) Wn (80,128) device fp32 -> out1 = out3 (128,128) = W X^T (K-major / MN-major B), out2 = out4 (128,80) = X Wn^T
+// (K-major / MN-major A), fp16 operands
+extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, float* out3, float* out4,
+                               void* stream) {
     using namespace neo;
-    const size_t smem = 32768 + 20480 + 64 + 1024;
+    const size_t smem = 86016 + 64 + 1024;
     NEO_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, W, Wn, out1, out2, nullptr);
+    tc::selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, W, Wn, out1, out2, out3, out4, nullptr);
     NEO_LAUNCH_CHECK("selftest_kernel");
     return NEO_OK;
 }

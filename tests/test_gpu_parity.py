@@ -262,11 +262,16 @@ def test_tc_primitives_selftest(cuda):
     Wn = torch.randn(80, 128, generator=g).to(cuda)
     o1 = torch.zeros(128, 128, device=cuda)
     o2 = torch.zeros(128, 80, device=cuda)
-    L.check(lib.neo_tc_selftest(L.ptr(X), L.ptr(W), L.ptr(Wn), L.ptr(o1), L.ptr(o2), torch.cuda.current_stream().cuda_stream))
+    o3 = torch.zeros(128, 128, device=cuda)
+    o4 = torch.zeros(128, 80, device=cuda)
+    L.check(lib.neo_tc_selftest(L.ptr(X), L.ptr(W), L.ptr(Wn), L.ptr(o1), L.ptr(o2), L.ptr(o3), L.ptr(o4), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     Xh, Wh, Wnh = X.half().float(), W.half().float(), Wn.half().float()
     assert md(o1, Wh @ Xh.T) < 1e-3
     assert md(o2, Xh @ Wnh.T) < 1e-3
+    print("MN-major B max err", md(o3, Wh @ Xh.T), " MN-major A max err", md(o4, Xh @ Wnh.T))
+    assert md(o3, Wh @ Xh.T) < 1e-3          # MN-major (point-contiguous) B operand, N=32 blocks at 64-byte offsets
+    assert md(o4, Xh @ Wnh.T) < 1e-3          # MN-major A operand, M=128 as two 64-point groups
 
 
 def test_field_eval_tc_vs_oracle(cuda):
