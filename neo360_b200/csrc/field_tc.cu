@@ -697,7 +697,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             uint32_t ph_h = 0, kcount = 0;      // bit b = parity of H_READY[b]
             long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0;
             TSTART();
-            const uint32_t id_blk = idesc_f16(128, 32), id_head = idesc_f16(128, 80), id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
+            // ENC (K-major, written by row owners) and H (MN-major = point-contiguous, written by neuron owners as 16-byte vectors)
+            const uint32_t id_blk = idesc_f16(128, 32), id_blk_mn = idesc_f16(128, 32, 0, 1), id_head = idesc_f16(128, 80, 1, 0),
+                           id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
             const uint32_t dD = tmem + TM_D, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
@@ -715,9 +717,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     for (int h = 0; h < 2; ++h, ++kcount) {
                         const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
                         const uint32_t sENC = sbase + SM_ENC + slot * SLOT_ENC;
-                        const uint32_t sHh = sH + h * (kHalfPts * 128);        // rows 64h.. of each 128-row slab
+                        const uint32_t sHh = sH + h * 16384;                    // MN-major tile of this half (64 points x 128 K)
                         uint64_t dENC[2], dHb[2];
-                        for (int bb = 0; bb < 2; ++bb) { dENC[bb] = desc_sw128(sENC + bb * 4096); dHb[bb] = desc_sw128(sHh + bb * 4096); }
+                        for (int bb = 0; bb < 2; ++bb) { dENC[bb] = desc_sw128(sENC + bb * 4096); dHb[bb] = desc_mn_sw128(sHh + bb * 64, 16384, 1024); }
                         TLAP(tm_issue);
                         mbar_wait(BAR(ENC_READY + slot), use, P.err, 10);
                         TLAP(tm_encwait);
@@ -737,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 wait_h(bb, 11);                     // layer l-1 of this block is in H
                                 if (elect_one()) {
 #pragma unroll
-                                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD + 32 * bb, aW + ks * 8, dk(dHb[bb], ks, 16384), id_blk, ks > 0);
+                                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD + 32 * bb, aW + ks * 8, dHb[bb] + (uint64_t)(ks * (2048 >> 4)), id_blk_mn, ks > 0);
                                     if (l == 3) {
 #pragma unroll
                                         for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, 1);
@@ -755,11 +757,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_ss(dH, desc_sw128(kaddr(sH, ks, 16384)), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
+                            mma_ss(dH, desc_mn_sw128(sH + ks * 2048, 16384, 1024), desc_sw128(kaddr(sWH + WH_H, ks, 10240)), id_head, (v > 0 || ks > 0));
                         if (v == nv - 1) {
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks)
-                                mma_ss(dH, desc_sw128(sDIR + ks * 32), desc_sw128(sWH + WH_DIR + ks * 32), id_head, 1);
+                                mma_ss(dH, desc_sw128(sDIR + ks * 32), desc_sw128(sWH + WH_DIR + ks * 32), idesc_f16(128, 80), 1);
                             tc_commit(BAR(HEAD_READY));
                             tc_commit(BAR(DIR_FREE));
                         }
@@ -798,16 +800,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         uint32_t ph_acc = 0, ph_head = 0, kcount = 0;     // bit b = parity of ACC_READY[b]
         long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
         TSTART();
-        uint32_t hoff[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hoff[j] = (uint32_t)(c >> 6) * 16384u + (uint32_t)(((((c & 63) >> 3) ^ j) << 4) + (c & 7) * 2);
+        const uint32_t hbase = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u;     // MN-major H: atom of 8 K rows, row c&7
         const uint32_t sH = sbase + SM_H, sBias = sbase + SM_BIAS;
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
                 for (int h = 0; h < 2; ++h, ++kcount) {
                     const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
-                    const uint32_t sHh = sH + h * (kHalfPts * 128);
+                    const uint32_t sHh = sH + h * 16384;
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
                         const float bias = lds_f32(sBias + 4 * (l * 128 + c));
@@ -827,11 +827,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             uint32_t r[32];
                             tmem_ld32(lane_base + TM_D + bb * 32, r);
                             tc_wait_ld();
-                            unsigned char* hp = sgen + (sHh - sbase) + bb * 32 * 128;
+                            unsigned char* hp = sgen + (sHh - sbase) + hbase;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float x = fmaxf(__uint_as_float(r[i]) + bias + gv[i], 0.f);
-                                *reinterpret_cast<__half*>(hp + i * 128 + hoff[i & 7]) = __float2half_rn(x);
+                            for (int j4 = 0; j4 < 4; ++j4) {          // 8 consecutive points = one 16-byte vector of this neuron's K row
+                                float x[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(r[8 * j4 + i]) + bias + gv[8 * j4 + i], 0.f);
+                                *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) =
+                                    make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
                             }
                             if (l == 3 && bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
                             tc_fence_before();
