@@ -129,3 +129,29 @@ def make_vanilla_params(seed: int = 0, density_bias_shift: float = 1.0) -> Dict[
             P[pre + name + ".weight"] = w
             P[pre + name + ".bias"] = b
     return P
+
+
+def make_mip_params(seed: int = 0, width: int = 1024) -> Dict[str, Tensor]:
+    """MipNeRF360 parameter set (models/mipnerf360/model.py:176-234): two PropMLPs (4x256, density only) and one NeRFMLP
+    (8 x `width`, default 1024) under the reference's state-dict names, plus the `pos_basis_t` buffers."""
+    from .mip_basis import POS_BASIS_T
+    g = torch.Generator().manual_seed(3000 + seed)
+    P: Dict[str, Tensor] = {}
+    for lvl in range(3):
+        pre = f"mlps.{lvl}."
+        w_, depth = (256, 4) if lvl < 2 else (width, 8)
+        P[pre + "pos_basis_t"] = POS_BASIS_T.clone()
+        shapes = {f"pts_linear.{i}": (w_, 504 if i == 0 else (w_ + 504 if (i == 5) else w_)) for i in range(depth)}
+        shapes["density_layer"] = (1, w_)
+        if lvl == 2:
+            shapes.update({"bottleneck_layer": (256, w_), "views_linear.0": (128, 283), "rgb_layer": (3, 128)})
+        for name, (o, i) in shapes.items():
+            bound = math.sqrt(6.0 / i)                      # kaiming_uniform_ (a=0), model.py:76-110
+            wgt = (torch.rand((o, i), generator=g) * 2 - 1) * bound
+            b = (torch.rand((o,), generator=g) * 2 - 1) / math.sqrt(i)
+            gain = {"density_layer": 0.6, "rgb_layer": 1.5}.get(name, 0.8)
+            if name == "density_layer":
+                b = b + 1.0
+            P[pre + name + ".weight"] = wgt * gain
+            P[pre + name + ".bias"] = b
+    return P

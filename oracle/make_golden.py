@@ -239,6 +239,55 @@ def vanilla(ns, path):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def mip360(ns, path):
+    """Golden vectors for the Mip-NeRF 360 renderer (row a18) from the unmodified reference MipNeRF360 module."""
+    from oracle import mip_oracle as mor
+    from neo360_b200.mip_basis import POS_BASIS_T
+    ref_basis = ns.mip_helper.generate_basis("icosahedron", 2)
+    assert maxdiff(POS_BASIS_T, ref_basis) == 0, "embedded basis != reference generate_basis"
+    out = {}
+    for tag, (W, H, B, npp, nn_, seed) in {"m_tiny": (64, 48, 40, 16, 8, 0), "m_small": (64, 48, 96, 32, 16, 1)}.items():
+        P = synth.make_mip_params(seed)
+        torch.manual_seed(seed)
+        net = ns.mip_model.MipNeRF360(num_prop_samples=npp, num_nerf_samples=nn_).eval()
+        net.load_state_dict(P, strict=True)
+        pose = synth.target_pose(9, 100)
+        dirs = ns.ray_utils.get_ray_directions(H, W, 0.8 * W)
+        ro, vd, rd, radii = ns.ray_utils.get_rays(dirs, pose[:3, :4], output_view_dirs=True, output_radii=True)
+        g = torch.Generator().manual_seed(70 + seed)
+        sel = torch.randperm(H * W, generator=g)[:B]
+        batch = {"rays_o": ro[sel].contiguous(), "rays_d": rd[sel].contiguous(), "viewdirs": vd[sel].contiguous(),
+                 "radii": radii[sel].reshape(-1, 1).contiguous()}
+        near, far = 0.2, 6.0
+        with torch.no_grad():
+            ren, hist = net(batch, 1.0, False, False, near, far)
+            jit = [torch.rand(B, 1, generator=g) for _ in range(3)]
+            with RandQueue(jit):
+                ren_r, hist_r = net(batch, 0.5, True, False, near, far)
+            o_ren, o_hist = mor.render(batch, P, POS_BASIS_T, npp, nn_, near, far, 1.0)
+            o_ren_r, o_hist_r = mor.render(batch, P, POS_BASIS_T, npp, nn_, near, far, 0.5, rand=jit)
+        worst = 0.0
+        for a, b, c, e in ((o_ren, o_hist, ren, hist), (o_ren_r, o_hist_r, ren_r, hist_r)):
+            for lvl in range(3):
+                worst = max(worst, maxdiff(a[lvl]["rgb"], c[lvl]["rgb"]))
+                for k in ("density", "rgb", "sdist", "weights"):
+                    worst = max(worst, maxdiff(b[lvl][k], e[lvl][k]))
+        assert worst < 5e-4, worst
+        print(f"mip360[{tag}]: oracle vs reference max|diff| = {worst:.3e}")
+        out.update({f"{tag}_cfg": np.array([W, H, B, npp, nn_, seed]), f"{tag}_near_far": np.array([near, far])})
+        for k, v in batch.items():
+            out[f"{tag}_{k}"] = v
+        for i in range(3):
+            out[f"{tag}_jit{i}"] = jit[i]
+            out[f"{tag}_eval{i}_rgb"] = ren[i]["rgb"]
+            out[f"{tag}_rand{i}_rgb"] = ren_r[i]["rgb"]
+            for k in ("density", "rgb", "sdist", "weights"):
+                out[f"{tag}_hist{i}_{k}"] = hist[i][k]
+            out[f"{tag}_rhist{i}_sdist"] = hist_r[i]["sdist"]
+    np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     ns = ref_shim.load()
     torch.set_grad_enabled(False)
@@ -252,6 +301,7 @@ def main():
     np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
     print("wrote", path, os.path.getsize(path), "bytes")
     vanilla(ns, os.path.join(GOLD, "vanilla_reference_vectors.npz"))
+    mip360(ns, os.path.join(GOLD, "mip360_reference_vectors.npz"))
 
 
 if __name__ == "__main__":

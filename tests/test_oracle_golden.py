@@ -117,3 +117,26 @@ def test_vanilla_oracle_vs_reference_vectors(vgolden, tag):
         for n_, a, b in zip(("rgb", "acc", "depth"), ev[lvl], rr[lvl]):
             assert md(a, g[f"{tag}_eval{lvl}_{n_}"]) < 1e-5, (lvl, n_)
             assert md(b, g[f"{tag}_rand{lvl}_{n_}"]) < 1e-5, (lvl, n_)
+
+
+# ---------------- Mip-NeRF 360 (row a18) ----------------
+
+@pytest.mark.parametrize("tag", ["m_tiny", "m_small"])
+def test_mip360_oracle_vs_reference_vectors(tag):
+    import os
+    from oracle import mip_oracle as mor
+    from neo360_b200.mip_basis import POS_BASIS_T
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mip360_reference_vectors.npz"))
+    W, H, B, npp, nn_, seed = [int(x) for x in g[f"{tag}_cfg"]]
+    near, far = [float(x) for x in g[f"{tag}_near_far"]]
+    P = synth.make_mip_params(seed)
+    batch = {k: T(g[f"{tag}_{k}"]) for k in ("rays_o", "rays_d", "viewdirs", "radii")}
+    with torch.no_grad():
+        ren, hist = mor.render(batch, P, POS_BASIS_T, npp, nn_, near, far, 1.0)
+        ren_r, hist_r = mor.render(batch, P, POS_BASIS_T, npp, nn_, near, far, 0.5, rand=[T(g[f"{tag}_jit{i}"]) for i in range(3)])
+    for i in range(3):
+        assert md(ren[i]["rgb"], g[f"{tag}_eval{i}_rgb"]) < 1e-4
+        assert md(ren_r[i]["rgb"], g[f"{tag}_rand{i}_rgb"]) < 1e-4
+        for k in ("density", "rgb", "sdist", "weights"):
+            assert md(hist[i][k], g[f"{tag}_hist{i}_{k}"]) < 1e-4, (i, k)
+        assert md(hist_r[i]["sdist"], g[f"{tag}_rhist{i}_sdist"]) < 1e-5
