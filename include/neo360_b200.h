@@ -212,6 +212,36 @@ size_t neo_vanilla_workspace_bytes(int n_rays, const NeoVanillaCfg* cfg);
 int neo_vanilla_render_fwd(const NeoVanilla* v, const NeoRays* rays, const NeoVanillaCfg* cfg, NeoVanillaOut* out,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Mip-NeRF 360: models/mipnerf360/model.py:30-365 ---- */
+typedef struct {
+    int depth, width;          /* PropMLP: 4 x 256 (density only), NeRFMLP: 8 x 1024 (model.py:176-195) */
+    const float* basis;        /* pos_basis_t (3,21) */
+    const float* w[8];         /* pts_linear.{i}.weight: (width,504), (width,width)..., layer 5 of a depth-8 MLP is (width, width+504) */
+    const float* b[8];
+    const float *wsig, *bsig;  /* density_layer (1,width) */
+    const float *wb, *bb;      /* bottleneck_layer (256,width)      -- NULL for a PropMLP (disable_rgb) */
+    const float *wv0, *bv0;    /* views_linear.0 (128, 256+27) */
+    const float *wrgb, *brgb;  /* rgb_layer (3,128) */
+} NeoMipMLPParams;
+typedef struct {
+    int n_prop, n_nerf;            /* MipNeRF360.num_prop_samples / num_nerf_samples (two proposal levels + one NeRF level) */
+    float near_plane, far_plane;   /* near / far passed to MipNeRF360.forward (model.py:236) */
+    float train_frac;              /* anneals the proposal logits (model.py:288-292) */
+    const float* jitter[3];        /* randomized: one (n_rays) uniform per level (single_jitter, helper.py:357-363); NULL = deterministic */
+} NeoMipCfg;
+typedef struct {                   /* per level: renderings[l]["rgb"], ray_history[l]{"density","rgb","sdist","weights"} (model.py:359-365) */
+    float* rgb[3];       /* (n_rays,3) */
+    float* density[3];   /* (n_rays,n_l) */
+    float* rgb_s[3];     /* (n_rays,n_l,3) -- zeros for the proposal levels */
+    float* sdist[3];     /* (n_rays,n_l+1) */
+    float* weights[3];   /* (n_rays,n_l) */
+} NeoMipOut;
+size_t neo_mip_workspace_bytes(int n_rays, const NeoMipCfg* cfg, int nerf_width);
+/* MipNeRF360.forward (models/mipnerf360/model.py:236-365); mlps[3] = {PropMLP, PropMLP, NeRFMLP}; radii (n_rays) */
+int neo_mip_render_fwd(const NeoMipMLPParams mlps[3], const float* rays_o, const float* rays_d, const float* viewdirs,
+                       const float* radii, int n_rays, const NeoMipCfg* cfg, NeoMipOut* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* bench support: CUDA events around every field-kernel launch on the launching stream + launch accounting.
  * neo_profile(1) resets and enables, neo_profile(0) resets and disables; neo_profile_read synchronises. */
 int neo_profile(int enable);

@@ -62,6 +62,23 @@ class NeoVanillaOut(C.Structure):
     _fields_ = [(n, C.c_void_p * 2) for n in VANILLA_OUT_FIELDS]
 
 
+class NeoMipMLPParams(C.Structure):
+    _fields_ = [("depth", C.c_int), ("width", C.c_int), ("basis", C.c_void_p), ("w", C.c_void_p * 8), ("b", C.c_void_p * 8)] + \
+               [(n, C.c_void_p) for n in ("wsig", "bsig", "wb", "bb", "wv0", "bv0", "wrgb", "brgb")]
+
+
+class NeoMipCfg(C.Structure):
+    _fields_ = [("n_prop", C.c_int), ("n_nerf", C.c_int), ("near_plane", C.c_float), ("far_plane", C.c_float), ("train_frac", C.c_float),
+                ("jitter", C.c_void_p * 3)]
+
+
+MIP_OUT_FIELDS = ("rgb", "density", "rgb_s", "sdist", "weights")
+
+
+class NeoMipOut(C.Structure):
+    _fields_ = [(n, C.c_void_p * 3) for n in MIP_OUT_FIELDS]
+
+
 # every symbol include/neo360_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "neo_scene_create": (C.c_int, [C.POINTER(NeoSceneDesc), C.POINTER(NeoMLPParams), C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
@@ -82,6 +99,9 @@ SYMBOLS = {
     "neo_vanilla_free": (None, [C.c_void_p]),
     "neo_vanilla_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(NeoVanillaCfg)]),
     "neo_vanilla_render_fwd": (C.c_int, [C.c_void_p, C.POINTER(NeoRays), C.POINTER(NeoVanillaCfg), C.POINTER(NeoVanillaOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "neo_mip_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(NeoMipCfg), C.c_int]),
+    "neo_mip_render_fwd": (C.c_int, [C.POINTER(NeoMipMLPParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(NeoMipCfg),
+                                     C.POINTER(NeoMipOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "neo_profile": (C.c_int, [C.c_int]),
     "neo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "neo_tc_selftest": (C.c_int, [C.c_void_p] * 8),
