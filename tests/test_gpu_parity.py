@@ -391,3 +391,86 @@ def test_mip360_vs_reference_vectors(cuda, tag):
             close(hist[i][k], g[f"{tag}_hist{i}_{k}"], (i, k))
         close(ren[i]["rgb"], g[f"{tag}_eval{i}_rgb"], (i, "rendering"))
         close(ren_r[i]["rgb"], g[f"{tag}_rand{i}_rgb"], (i, "rendering rand"))
+
+
+# ---------------- edge cases of the NeO-360 path ----------------
+
+def _frame_rays(W, H, view=3):
+    pose = synth.target_pose(view, 100)
+    ro, vd, rd, _ = orc.rays_from_pose(orc.ray_directions(H, W, 0.8 * W), pose[:3, :4])
+    return {"rays_o": ro, "rays_d": rd, "viewdirs": vd}
+
+
+@pytest.mark.parametrize("nv", [1, 2, 4])
+def test_other_source_view_counts(cuda, nv):
+    """NV != 3 source views (NeRF_TP(num_src_views=...), model.py:173): fp32 within 2e-4 of the oracle, TC within 3e-2."""
+    from neo360_b200 import NeRF_TP
+    W, H, nc, nf = 64, 48, 16, 8
+    sc = synth.make_scene((W, H), nv, (24, 32), 5)
+    P = synth.make_mlp_params(5)
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+    rays = {k: v[700:700 + 50].contiguous() for k, v in _frame_rays(W, H).items()}
+    with torch.no_grad():
+        ref = orc.render(rays, osc, P, nc, nf, False, True)[1]
+    net = NeRF_TP(num_coarse_samples=nc, num_fine_samples=nf, num_src_views=nv, precision="fp32").eval()
+    net.load_state_dict(P)
+    net = net.to(cuda)
+    net.set_scene(*[sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")],
+                  sc["img_wh"], precisions=["fp32", "tc"])
+    cr = {k: v.to(cuda) for k, v in rays.items()}
+    for prec, tol in (("fp32", 3e-4), ("tc", 3e-2)):
+        net.precision = prec
+        with torch.no_grad():
+            got = net(cr, False, False, None, None, out_depth=True)[1]
+        net.check()
+        assert md(got[0], ref[0]) < tol and md(got[5], ref[5]) < tol, (prec, md(got[0], ref[0]))
+
+
+def test_reference_default_sample_counts_and_ragged_sizes(cuda):
+    """NeRF_TP defaults 128 + 256 samples (model.py:169-171 => 129 / 385 points) on 33 rays (one full TC ray group + one ray),
+    and a single ray; fp32 vs oracle 3e-4, TC vs fp32 3e-2."""
+    net, osc, P = make_net(cuda, (64, 48), (24, 32), 128, 256, 3, precisions=("fp32", "tc"))
+    for n in (33, 1):
+        rays = {k: v[1500:1500 + n].contiguous() for k, v in _frame_rays(64, 48).items()}
+        with torch.no_grad():
+            ref = orc.render(rays, osc, P, 128, 256, False, True)[1]
+        cr = {k: v.to(cuda) for k, v in rays.items()}
+        res = {}
+        for prec in ("fp32", "tc"):
+            net.precision = prec
+            with torch.no_grad():
+                res[prec] = net(cr, False, False, None, None, out_depth=True)[1]
+            net.check()
+        assert md(res["fp32"][0], ref[0]) < 3e-4, n
+        assert md(res["tc"][0], res["fp32"][0].cpu()) < 3e-2, n
+
+
+def test_ray_missing_the_sphere_is_reported(cuda):
+    """The reference asserts (helper.py:271); here the error is deferred to NeRF_TP.check()."""
+    net, osc, P = make_net(cuda, (64, 48), (24, 32), 8, 4, 0)
+    rays = {"rays_o": torch.tensor([[2.0, 0.0, 0.0]], device=cuda), "rays_d": torch.tensor([[0.0, 1.0, 0.0]], device=cuda),
+            "viewdirs": torch.tensor([[0.0, 1.0, 0.0]], device=cuda)}
+    with torch.no_grad():
+        net(rays, False, False, None, None, out_depth=True)
+    with pytest.raises(RuntimeError, match="unit sphere"):
+        net.check()
+    net.check()      # flag is cleared after being reported
+
+
+def test_tc_randomized_and_train_tuple(cuda, golden):
+    """TC path with the reference's injected uniforms and the train-mode tuple layout (weights / sdist), vs reference vectors."""
+    g = golden
+    tag = "small"
+    W, H, hp, wp, B, nc, nf, seed, start = [int(x) for x in g[f"{tag}_cfg"]]
+    net, osc, P = make_net(cuda, (W, H), (hp, wp), nc, nf, seed, precisions=("tc",), precision="tc")
+    rays = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs")}
+    rays_r = dict(rays)
+    rays_r["_uniforms"] = [T(g[f"{tag}_u_{k}"]).to(cuda) for k in ("fg0", "bg0", "fg1", "bg1")]
+    with torch.no_grad():
+        rr = net(rays_r, True, False, None, None, out_depth=True)
+        tr = net(rays, False, True, None, None, out_depth=False)
+    net.check()
+    assert md(rr[1][0], T(g[f"{tag}_rand1_comp_rgb"])) < 3e-2 and md(rr[0][0], T(g[f"{tag}_rand0_comp_rgb"])) < 3e-2
+    assert tr[1][1].shape == (B, nc + 1 + nf) and md(tr[0][3], T(g[f"{tag}_train0_fg_sdist"])) < 1e-6     # coarse sdist is exact
+    assert md(tr[0][1], T(g[f"{tag}_train0_fg_w"])) < 3e-2 and md(tr[1][0], T(g[f"{tag}_train1_comp_rgb"])) < 3e-2
