@@ -257,6 +257,8 @@ int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1
 /* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 16)
  * int64; NULL disables.  Roles and slots are documented in csrc/field_tc.cu. */
 int neo_tc_debug(long long* buf);
+/* Debug: sensitivity experiments for profiling -- the TC kernel skips parts of its work (results become wrong); 0 = normal. */
+int neo_tc_ablate(int mask);
 
 const char* neo_last_error(void);
 /* "neo360_b200 <version> sm_100a" */

@@ -80,6 +80,7 @@ struct Params {
     float* sigma_out;
     int* err;
     long long* dbg;     // optional [gridDim.x][16] cycle counters (neo_tc_debug), null in production
+    int ablate;         // debug only (neo_tc_ablate): 1 no tap loads, 2 no pos-enc math, 4 no G reads in the epilogue, 8 no MMAs
 };
 
 // cycle accounting for neo_tc_debug (one representative thread per role); compiled in, costs two CS2R when enabled
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                         for (int c = 0; c < KE / 8; ++c) {
                             if ((c & 3) == sub) {
-                                const uint4 pk = enc_chunk<ICH>(c, ce);
+                                const uint4 pk = (P.ablate & 2) ? make_uint4(0u, 0u, 0u, 0u) : enc_chunk<ICH>(c, ce);
                                 sts128(encb + (c >> 3) * SLAB_ENC + row * 128 + (((c & 7) ^ (row & 7)) << 4), pk);
                             }
                         }
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
                                 const uint4 off = lds128(rowtab + r * 128 + m * 32);
-                                live[m] = off.x != 0xFFFFFFFFu;         // warp-uniform: out-of-range lookups contribute exact zeros
+                                live[m] = off.x != 0xFFFFFFFFu && !(P.ablate & 1);         // warp-uniform: out-of-range lookups contribute exact zeros
                                 if (live[m]) {
                                     val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
                                     val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
@@ -811,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
                         const float bias = lds_f32(sBias + 4 * (l * 128 + c));
-                        const bool hasG = (l == 0) | (l == 3);
+                        const bool hasG = ((l == 0) | (l == 3)) && !(P.ablate & 4);
                         const __half* gbase = reinterpret_cast<const __half*>(sgen + (l == 0 ? SM_G0 : SM_G3) + slot * SLOT_G) + c;   // G[slot][0][c]
 #pragma unroll 1
                         for (int bb = 0; bb < 2; ++bb) {
@@ -1073,6 +1074,7 @@ void tc_scene_free(NeoScene* sc) {
 }
 
 static long long* g_dbg = nullptr;   // set by neo_tc_debug
+static int g_ablate = 0;             // set by neo_tc_ablate (debug)
 
 int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mlp_index,
                     float* rgb, float* sigma, cudaStream_t s) {
@@ -1099,6 +1101,7 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
     P.mlp = st->mlp[mlp_index];
     P.rgb_out = rgb; P.sigma_out = sigma; P.err = sc->err_flag;
     P.dbg = g_dbg;
+    P.ablate = g_ablate;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
     const size_t smem = SM_TOTAL + 1024;
     if (mlp_index & 1) {
@@ -1130,3 +1133,5 @@ extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, 
 // Per CTA: [0] pts [1] wait ENC_FREE [2] geometry [3] producer bar [4] wait G_FREE [5] gather | [6] MMA wait ENC_READY
 // [7] MMA wait H_READY [8] MMA issue | [9] epi wait ACC [10] epi wait G [11] epi work [12] epi head
 extern "C" int neo_tc_debug(long long* buf) { neo::g_dbg = buf; return NEO_OK; }
+// Debug: sensitivity experiments -- the kernel skips parts of its work (results become wrong!): see Params::ablate.
+extern "C" int neo_tc_ablate(int mask) { neo::g_ablate = mask; return NEO_OK; }

@@ -6,6 +6,7 @@ import bench
 from neo360_b200 import NeRF_TP, _lib as L
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+ablate = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = torch.device("cuda:0")
 sc, P = bench.build_scene_cpu()
 net = NeRF_TP(num_coarse_samples=128, num_fine_samples=64, precision="tc").eval()
@@ -16,6 +17,7 @@ rays = {"rays_o": o[:n].to(dev), "rays_d": d[:n].to(dev), "viewdirs": d[:n].to(d
 lib = L.load()
 with torch.no_grad():
     net.render_rays_test(rays, chunk=1024)
+    lib.neo_tc_ablate(ablate)
     buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     lib.neo_tc_debug(buf.data_ptr())
     torch.cuda.synchronize()
@@ -29,6 +31,7 @@ names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P wait G_FREE", "P 
 # counters are overwritten by each of the 4 field launches: they hold the LAST launch (bg fine, N=193)
 tiles = ((n + 31) // 32) * ((193 + 3) // 4)
 halfjobs_per_cta = tiles * 6 / 148
-print(f"{n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
+lib.neo_tc_ablate(0)
+print(f"ablate={ablate}: {n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
 for i, nm in enumerate(names):
     print(f"  {nm:18s} {b[:, i].mean() / halfjobs_per_cta:9.0f} cycles / half-job   (total {b[:, i].mean() / 1e6:8.2f} Mcyc)")
