@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = sbase + SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + SM_BAR + 8 * NUM_BARS);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + SM_BAR + 8 * NUM_BARS);     // [NUM_BARS]: TMEM base, [NUM_BARS+1]: TMA barrier
 
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
@@ -467,11 +467,20 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) tmem_alloc(sbase + SM_BAR + 8 * NUM_BARS, 512);
-    {   // head weights + biases -> smem
-        const uint4* src = P.mlp.headimg;
-        for (int i = threadIdx.x; i < (int)(WH_BYTES / 16); i += kThreads) sts128(sbase + SM_WHEAD + 16 * i, __ldg(src + i));
-        float* bsm = reinterpret_cast<float*>(sgen + SM_BIAS);
-        for (int i = threadIdx.x; i < BIAS_FLOATS; i += kThreads) bsm[i] = __ldg(P.mlp.bias + i);
+    {   // head weights (pre-swizzled UMMA tiles) + biases -> smem with one TMA bulk copy each (cp.async.bulk, mbarrier tx-count)
+        const uint32_t tbar = BAR(NUM_BARS + 1);
+        if (threadIdx.x == 0) {
+            mbar_init(tbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = WH_BYTES + BIAS_FLOATS * 4;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + SM_WHEAD), "l"(P.mlp.headimg), "r"((uint32_t)WH_BYTES), "r"(tbar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + SM_BIAS), "l"(P.mlp.bias), "r"((uint32_t)(BIAS_FLOATS * 4)), "r"(tbar) : "memory");
+        }
+        __syncthreads();
+        mbar_wait(tbar, 0, P.err, 90);
         float* vsm = reinterpret_cast<float*>(sgen + SM_VIEWS);
         const float* vsrc = reinterpret_cast<const float*>(P.sc.views);
         for (int i = threadIdx.x; i < P.nv * 16; i += kThreads) vsm[i] = __ldg(vsrc + i);
