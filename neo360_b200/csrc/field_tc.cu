@@ -47,7 +47,8 @@ constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB =
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t TM_D = 0;        // trunk accumulator (128) ; also Dq (64) / Drgb (16)
+constexpr uint32_t TM_D = 0;        // trunk accumulator of layers 0-2 (2 blocks x 32 points) ; also Dq (64) / Drgb (16)
+constexpr uint32_t TM_D3 = 64;      // layer-3 accumulator (2 x 32): seeded with W3enc.ENC at layer-0 time so the ENC / G slots free early
 constexpr uint32_t TM_DH = 128;     // head accumulator (80)
 constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
 
@@ -84,8 +85,13 @@ struct Params {
 };
 
 // cycle accounting for neo_tc_debug (one representative thread per role); compiled in, costs two CS2R when enabled
-#define TSTART() long long _t0 = clock64()
-#define TLAP(acc) do { long long _t1 = clock64(); acc += _t1 - _t0; _t0 = _t1; } while (0)
+#ifndef NEO_PROD_SLEEP_NS
+#define NEO_PROD_SLEEP_NS 100
+#endif
+constexpr int kProdSleep = NEO_PROD_SLEEP_NS;
+// cycle accounting (neo_tc_debug): compiled only into the DBG instantiation of the kernel
+#define TSTART() long long _t0 = DBG ? clock64() : 0
+#define TLAP(acc) do { if (DBG) { long long _t1 = clock64(); acc += _t1 - _t0; _t0 = _t1; } } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -112,22 +118,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Wait on an mbarrier phase: asm loop with an in-register spin bound, so a protocol bug traps (launch failure reported by
+// neo_check_async / the next CUDA call) instead of hanging the GPU.  SLEEP_NS > 0 backs off between polls: used by the producer
+// warps, which run ahead of the tensor pipeline and must not steal issue slots from the epilogue warps sharing their schedulers.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {                 // each failed try_wait suspends the warp for a while: >> 1 s in total
-            if (err) atomicExch(err, 1000 + tag);
-            __trap();
-        }
+    (void)err; (void)tag;
+    if (SLEEP_NS > 0) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
+            "mov.u32 c, 0;\n\t"
+            "NEO_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+            "@p bra NEO_DONE_%=;\n\t"
+            "nanosleep.u32 %3;\n\t"
+            "add.u32 c, c, 1;\n\t"
+            "setp.lt.u32 q, c, 0x4000000;\n\t"
+            "@q bra NEO_WAIT_%=;\n\t"
+            "trap;\n\t"
+            "NEO_DONE_%=:\n\t}"
+            ::"r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)SLEEP_NS) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
+            "mov.u32 c, 0;\n\t"
+            "NEO_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+            "@p bra NEO_DONE_%=;\n\t"
+            "add.u32 c, c, 1;\n\t"
+            "setp.lt.u32 q, c, 0x8000000;\n\t"
+            "@q bra NEO_WAIT_%=;\n\t"
+            "trap;\n\t"
+            "NEO_DONE_%=:\n\t}"
+            ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
     }
-}
-// Group wait: ONE warp polls the mbarrier, the rest of the group blocks on a hardware named barrier (no polling instructions:
-// a dozen warps spinning on try_wait were eating ~40 % of the SM's issue slots).  bar.sync orders memory for the whole group.
-__device__ __forceinline__ void group_wait(uint32_t bar, uint32_t parity, bool poller, int bar_id, int nthreads, int* err, int tag) {
-    if (poller) mbar_wait(bar, parity, err, tag);
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
 }
 // one lane of a fully converged warp (the MMA warp keeps warp-uniform control flow so descriptors stay in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -438,7 +462,7 @@ __device__ __forceinline__ uint4 enc_chunk(int c, const float* x) {
     return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
 
-template <int ICH>
+template <int ICH, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -552,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     if (v == nv - 1) {
                         // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360);
                         //      written with the LAST view so the previous tile's head MMA has long released the DIR tile ----
-                        if (h == 0) { mbar_wait(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
+                        if (h == 0) { mbar_wait<kProdSleep>(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
                         const int dt = ptid - (kProducerWarps * 32 - 4 * 32);       // last 4 producer warps: 128 threads = 64 rows x 2
                         if (dt >= 0) {
                             const int row = dt & (kHalfPts - 1), sub = dt >> 6;      // sub warp-uniform
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         }
                     }
                     // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved), thread = (sub, row) ----
-                    mbar_wait(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
+                    mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
                     TLAP(tp_encwait);
                     if (ptid < 4 * kHalfPts) {
                         // sub is warp-uniform (64 consecutive threads share it): no divergence between the map / chunk variants
@@ -650,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                         for (int m = 1; m < 4; ++m)
                             mapbase[m] = reinterpret_cast<const uint4*>(P.mlp.pplane[m - 1] + (size_t)v * pl_hw * 256) + lane;
-                        mbar_wait(BAR(G_FREE + slot), use ^ 1, P.err, 3);
+                        mbar_wait<kProdSleep>(BAR(G_FREE + slot), use ^ 1, P.err, 3);
                         TLAP(tp_gwait);
                         const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + (lane & 15) * 16;
 #pragma unroll 1
@@ -694,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 }
             }
         }
-        if (P.dbg && ptid == 0) {
+        if (DBG && P.dbg && ptid == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * 16;
             d[0] = tp_pts; d[1] = tp_encwait; d[2] = tp_geom; d[3] = tp_bar; d[4] = tp_gwait; d[5] = tp_gather;
         }
@@ -710,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             // ENC (K-major, written by row owners) and H (MN-major = point-contiguous, written by neuron owners as 16-byte vectors)
             const uint32_t id_blk = idesc_f16(128, 32), id_blk_mn = idesc_f16(128, 32, 0, 1), id_head = idesc_f16(128, 80, 1, 0),
                            id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
-            const uint32_t dD = tmem + TM_D, dH = tmem + TM_DH;
+            const uint32_t dD = tmem + TM_D, dD3 = tmem + TM_D3, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
@@ -739,8 +763,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             for (int bb = 0; bb < 2; ++bb) {
 #pragma unroll
                                 for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW0 + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
+                                // skip connection of layer 3 (model.py:142-146): its encoding part is accumulated NOW into a second
+                                // accumulator, so the ENC slot is released after layer 0 instead of after layer 3
+#pragma unroll
+                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3 + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
                                 tc_commit(BAR(ACC_READY + bb));
                             }
+                            tc_commit(BAR(ENC_FREE + slot));
                         }
                         __syncwarp();
                         for (int l = 1; l <= 3; ++l) {
@@ -749,13 +778,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 wait_h(bb, 11);                     // layer l-1 of this block is in H
                                 if (elect_one()) {
 #pragma unroll
-                                    for (int ks = 0; ks < 8; ++ks) mma_ts(dD + 32 * bb, aW + ks * 8, dHb[bb] + (uint64_t)(ks * (2048 >> 4)), id_blk_mn, ks > 0);
-                                    if (l == 3) {
-#pragma unroll
-                                        for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, 1);
-                                    }
+                                    for (int ks = 0; ks < 8; ++ks)
+                                        mma_ts((l == 3 ? dD3 : dD) + 32 * bb, aW + ks * 8, dHb[bb] + (uint64_t)(ks * (2048 >> 4)), id_blk_mn, (l == 3) || ks > 0);
                                     tc_commit(BAR(ACC_READY + bb));
-                                    if (l == 3 && bb == 1) tc_commit(BAR(ENC_FREE + slot));
                                 }
                                 __syncwarp();
                             }
@@ -796,7 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 // accumulator drained by the colour epilogue before the next tile overwrites it
                 wait_h(0, 16);
             }
-            if (P.dbg && lane == 0) {
+            if (DBG && P.dbg && lane == 0) {
                 long long* d = P.dbg + (size_t)blockIdx.x * 16;
                 d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue;
             }
@@ -820,9 +845,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     const uint32_t sHh = sH + h * 16384;
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
-                        const float bias = lds_f32(sBias + 4 * (l * 128 + c));
-                        const bool hasG = ((l == 0) | (l == 3)) && !(P.ablate & 4);
-                        const __half* gbase = reinterpret_cast<const __half*>(sgen + (l == 0 ? SM_G0 : SM_G3) + slot * SLOT_G) + c;   // G[slot][0][c]
+                        // layer 3: bias and gathered part were folded into its accumulator during the layer-0 epilogue (below)
+                        const float bias = (l == 3) ? 0.f : lds_f32(sBias + 4 * (l * 128 + c));
+                        const bool hasG = (l == 0) && !(P.ablate & 4);
+                        const __half* gbase = reinterpret_cast<const __half*>(sgen + SM_G0 + slot * SLOT_G) + c;    // G0[slot][0][c]
+                        const __half* g3base = reinterpret_cast<const __half*>(sgen + SM_G3 + slot * SLOT_G) + c;   // G3[slot][0][c]
 #pragma unroll 1
                         for (int bb = 0; bb < 2; ++bb) {
                             if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); TLAP(te_gwait); }
@@ -835,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             TLAP(te_accwait);
                             tc_fence_after();
                             uint32_t r[32];
-                            tmem_ld32(lane_base + TM_D + bb * 32, r);
+                            tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
                             tc_wait_ld();
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
 #pragma unroll
@@ -846,7 +873,21 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) =
                                     make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
                             }
-                            if (l == 3 && bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
+                            if (l == 0) {
+                                // layer-3 accumulator (already W3enc.ENC): += b3 + G3, in place in TMEM; after this nothing of the
+                                // gather slot is needed any more, so the producers get it back ~one job earlier
+                                const float b3 = lds_f32(sBias + 4 * (3 * 128 + c));
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(g3base[(bb * 32 + i) * 128]);
+                                tmem_ld32(lane_base + TM_D3 + bb * 32, r);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + b3 + gv[i]);
+                                tmem_st16(lane_base + TM_D3 + bb * 32, r);
+                                tmem_st16(lane_base + TM_D3 + bb * 32 + 16, r + 16);
+                                tc_wait_st();
+                                if (bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
+                            }
                             tc_fence_before();
                             fence_proxy_async();
                             mbar_arrive_warp(BAR(H_READY + bb), lane);
@@ -915,7 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             tc_fence_before(); mbar_arrive_warp(BAR(H_READY), lane);
             TLAP(te_head);
         }
-        if (P.dbg && threadIdx.x == 0) {
+        if (DBG && P.dbg && threadIdx.x == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * 16;
             d[9] = te_accwait; d[10] = te_gwait; d[11] = te_work; d[12] = te_head;
         }
@@ -1113,13 +1154,15 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
     P.ablate = g_ablate;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
     const size_t smem = SM_TOTAL + 1024;
-    if (mlp_index & 1) {
-        NEO_CUDA(cudaFuncSetAttribute(field_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        field_tc_kernel<4><<<grid, kThreads, smem, s>>>(P);
-    } else {
-        NEO_CUDA(cudaFuncSetAttribute(field_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        field_tc_kernel<3><<<grid, kThreads, smem, s>>>(P);
-    }
+    auto launch = [&](auto kern) -> int {
+        NEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, s>>>(P);
+        return NEO_OK;
+    };
+    int rc;
+    if (mlp_index & 1) rc = g_dbg ? launch(field_tc_kernel<4, true>) : launch(field_tc_kernel<4, false>);
+    else rc = g_dbg ? launch(field_tc_kernel<3, true>) : launch(field_tc_kernel<3, false>);
+    if (rc != NEO_OK) return rc;
     NEO_LAUNCH_CHECK("field_tc_kernel");
     return NEO_OK;
 }
