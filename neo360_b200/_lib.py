@@ -119,10 +119,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m neo360_b200.build` (or __graft_entry__.build()); "
+    path = os.environ.get("NEO360_B200_LIB", LIB_PATH)      # override: A/B runs of experimental kernel builds (tools/)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m neo360_b200.build` (or __graft_entry__.build()); "
                            "there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -42,7 +42,8 @@ constexpr uint32_t SM_BIAS = 204800;      // fp32: b0..b3 (512) | bq (64) | bv1 
 constexpr uint32_t SM_PTS = 207872;       // per-tile cache: 128 rows x 48 B (world points are view independent)
 constexpr uint32_t SM_VIEWS = 214016;     // kMaxViews x 64 B source-camera transforms
 constexpr uint32_t SM_BAR = 214528;
-constexpr uint32_t SM_TOTAL = 214784;
+constexpr uint32_t SM_SEL = 215040;       // 32 x 128 B one-hot selector tile (SW128): B operand of the bias MMA, k-step l selects layer l
+constexpr uint32_t SM_TOTAL = 219136;
 constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB = 8192;
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 
@@ -50,6 +51,7 @@ constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 constexpr uint32_t TM_D = 0;        // trunk accumulator of layers 0-2 (2 blocks x 32 points) ; also Dq (64) / Drgb (16)
 constexpr uint32_t TM_D3 = 64;      // layer-3 accumulator (2 x 32): seeded with W3enc.ENC at layer-0 time so the ENC / G slots free early
 constexpr uint32_t TM_DH = 128;     // head accumulator (80)
+constexpr uint32_t TM_BIAS = 208;   // A tile (K = 16) of the bias MMA: k = l holds the bias of trunk layer l (fp16)
 constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
 
 // slot-indexed barriers come in pairs (slot 0, slot 1)
@@ -524,7 +526,31 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             for (int i = 0; i < 16; ++i) r[i] = __ldg(P.mlp.wimg + (size_t)(j0 + i) * 128 + n);
             tmem_st16(tw + j0, r);
         }
+        // trunk biases enter the accumulators through one extra K=16 MMA per block-layer (A = this tile, B = one-hot selector),
+        // which removes 32 FADDs per block-layer from the issue-bound epilogue warps
+        {
+            const float* bs = reinterpret_cast<const float*>(sgen + SM_BIAS);
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = 0u;
+            r[0] = pack_h2(bs[n], bs[128 + n]);
+            r[1] = pack_h2(bs[256 + n], bs[384 + n]);
+            tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + TM_BIAS, r);
+        }
         tc_wait_st();
+    } else if (warp >= kProducerWarp0) {
+        const int ptid0 = threadIdx.x - kProducerWarp0 * 32;
+        if (ptid0 < 256) {   // selector tile: row n (point), logical k = 17 l  <->  k-step l, element l   is 1.0
+            const int row = ptid0 >> 3, chunk = ptid0 & 7;
+            uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            if ((chunk & 1) == 0) {
+                const int l = chunk >> 1;                         // logical byte 34 l: chunk 2l, half-word l
+                const uint32_t one = 0x3C00u << (16 * (l & 1));
+                if ((l >> 1) == 0) z.x = one; else z.y = one;
+            }
+            *reinterpret_cast<uint4*>(sgen + SM_SEL + row * 128 + ((chunk ^ (row & 7)) << 4)) = z;
+        }
+        fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
@@ -737,6 +763,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             const uint32_t dD = tmem + TM_D, dD3 = tmem + TM_D3, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
+            const uint32_t aB = tmem + TM_BIAS;
+            const uint64_t dSEL = desc_sw128(sbase + SM_SEL);          // + 2 l: k-step l = one-hot of layer l
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
             // descriptor of k-step ks = base descriptor + ((ks>>2)*slab + (ks&3)*32) / 16 in the start-address field
             auto dk = [](uint64_t base, int ks, uint32_t slab_bytes) { return base + (uint64_t)(((uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u) >> 4); };
@@ -767,6 +795,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 // accumulator, so the ENC slot is released after layer 0 instead of after layer 3
 #pragma unroll
                                 for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3 + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
+                                mma_ts(dD + 32 * bb, aB, dSEL, id_blk, 1);              // + b0
+                                mma_ts(dD3 + 32 * bb, aB, dSEL + 6, id_blk, 1);         // + b3
                                 tc_commit(BAR(ACC_READY + bb));
                             }
                             tc_commit(BAR(ENC_FREE + slot));
@@ -780,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                                     for (int ks = 0; ks < 8; ++ks)
                                         mma_ts((l == 3 ? dD3 : dD) + 32 * bb, aW + ks * 8, dHb[bb] + (uint64_t)(ks * (2048 >> 4)), id_blk_mn, (l == 3) || ks > 0);
+                                    if (l < 3) mma_ts(dD + 32 * bb, aB, dSEL + (uint64_t)(2 * l), id_blk, 1);     // + b_l
                                     tc_commit(BAR(ACC_READY + bb));
                                 }
                                 __syncwarp();
@@ -845,48 +876,69 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     const uint32_t sHh = sH + h * 16384;
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
-                        // layer 3: bias and gathered part were folded into its accumulator during the layer-0 epilogue (below)
-                        const float bias = (l == 3) ? 0.f : lds_f32(sBias + 4 * (l * 128 + c));
-                        const bool hasG = (l == 0) && !(P.ablate & 4);
+                        // biases arrive through the bias MMA; layer 3's gathered part was folded into its accumulator during the
+                        // layer-0 epilogue (below), so layers 1-3 are: TMEM load -> fp16 pack -> packed ReLU -> 4 x 16-byte stores
                         const __half* gbase = reinterpret_cast<const __half*>(sgen + SM_G0 + slot * SLOT_G) + c;    // G0[slot][0][c]
                         const __half* g3base = reinterpret_cast<const __half*>(sgen + SM_G3 + slot * SLOT_G) + c;   // G3[slot][0][c]
+                        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll 1
                         for (int bb = 0; bb < 2; ++bb) {
                             if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); TLAP(te_gwait); }
-                            // gathered features of this block first (plain shared loads, all in flight), then the accumulator
-                            float gv[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) gv[i] = hasG ? __half2float(gbase[(bb * 32 + i) * 128]) : 0.f;
-                            TLAP(te_work);
-                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
-                            TLAP(te_accwait);
-                            tc_fence_after();
-                            uint32_t r[32];
-                            tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
-                            tc_wait_ld();
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {          // 8 consecutive points = one 16-byte vector of this neuron's K row
-                                float x[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(r[8 * j4 + i]) + bias + gv[8 * j4 + i], 0.f);
-                                *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) =
-                                    make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
-                            }
+                            uint32_t r[32];
                             if (l == 0) {
-                                // layer-3 accumulator (already W3enc.ENC): += b3 + G3, in place in TMEM; after this nothing of the
+                                // gathered features of this block first (plain shared loads, all in flight), then the accumulator
+                                float gv[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(gbase[(bb * 32 + i) * 128]);
+                                TLAP(te_work);
+                                mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20); ph_acc ^= 1u << bb;
+                                TLAP(te_accwait);
+                                tc_fence_after();
+                                tmem_ld32(lane_base + TM_D + bb * 32, r);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {          // 8 consecutive points = one 16-byte vector of this neuron's K row
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const uint32_t pk = pack_h2(__uint_as_float(r[8 * j4 + 2 * i]) + gv[8 * j4 + 2 * i],
+                                                                    __uint_as_float(r[8 * j4 + 2 * i + 1]) + gv[8 * j4 + 2 * i + 1]);
+                                        const __half2 hv = __hmax2(*reinterpret_cast<const __half2*>(&pk), zero2);
+                                        w[i] = *reinterpret_cast<const uint32_t*>(&hv);
+                                    }
+                                    *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
+                                // layer-3 accumulator (already W3enc.ENC + b3): += G3, in place in TMEM; after this nothing of the
                                 // gather slot is needed any more, so the producers get it back ~one job earlier
-                                const float b3 = lds_f32(sBias + 4 * (3 * 128 + c));
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(g3base[(bb * 32 + i) * 128]);
                                 tmem_ld32(lane_base + TM_D3 + bb * 32, r);
                                 tc_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + b3 + gv[i]);
+                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + gv[i]);
                                 tmem_st16(lane_base + TM_D3 + bb * 32, r);
                                 tmem_st16(lane_base + TM_D3 + bb * 32 + 16, r + 16);
                                 tc_wait_st();
                                 if (bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
+                            } else {
+                                TLAP(te_work);
+                                mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
+                                TLAP(te_accwait);
+                                tc_fence_after();
+                                tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const uint32_t pk = pack_h2(__uint_as_float(r[8 * j4 + 2 * i]), __uint_as_float(r[8 * j4 + 2 * i + 1]));
+                                        const __half2 hv = __hmax2(*reinterpret_cast<const __half2*>(&pk), zero2);
+                                        w[i] = *reinterpret_cast<const uint32_t*>(&hv);
+                                    }
+                                    *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
                             }
                             tc_fence_before();
                             fence_proxy_async();
