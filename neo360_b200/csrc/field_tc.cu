@@ -82,7 +82,7 @@ struct Params {
     float* rgb_out;
     float* sigma_out;
     int* err;
-    long long* dbg;     // optional [gridDim.x][16] cycle counters (neo_tc_debug), null in production
+    long long* dbg;     // optional [gridDim.x][kDbgStride] cycle counters (neo_tc_debug), null in production
     int ablate;         // debug only (neo_tc_ablate): 1 no tap loads, 2 no pos-enc math, 4 no G reads in the epilogue, 8 no MMAs
 };
 
@@ -91,6 +91,7 @@ struct Params {
 #define NEO_PROD_SLEEP_NS 100
 #endif
 constexpr int kProdSleep = NEO_PROD_SLEEP_NS;
+constexpr int kDbgStride = 64;
 // cycle accounting (neo_tc_debug): compiled only into the DBG instantiation of the kernel
 #define TSTART() long long _t0 = DBG ? clock64() : 0
 #define TLAP(acc) do { if (DBG) { long long _t1 = clock64(); acc += _t1 - _t0; _t0 = _t1; } } while (0)
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         uint32_t ph_dir_free = 1;
         uint32_t kcount = 0;
         long long tp_pts = 0, tp_encwait = 0, tp_geom = 0, tp_gwait = 0, tp_gather = 0, tp_bar = 0;
+        long long tp_enc_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp_gf_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp_ga_j[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         TSTART();
         PtsRow* pts = reinterpret_cast<PtsRow*>(sgen + SM_PTS);
         const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
@@ -655,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     }
                     // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved), thread = (sub, row) ----
                     mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
+                    if (DBG) { long long t1 = clock64(); tp_enc_j[(v * 2 + h) % 8] += t1 - _t0; }
                     TLAP(tp_encwait);
                     if (ptid < 4 * kHalfPts) {
                         // sub is warp-uniform (64 consecutive threads share it): no divergence between the map / chunk variants
@@ -677,7 +680,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         }
                         // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w)
                         const bool dead = (tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f);   // zeros padding
-                        sts128(rowtab + row * 128 + sub * 32, make_uint4(dead ? 0xFFFFFFFFu : (uint32_t)(tp.idx[0] * 32), tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
+                        // bit 0 of the first offset: "same texel quad as the previous row" (rows are consecutive lanes; the gather
+                        // then keeps the four texels in registers).  Never set on lane 0 or after a dead row.
+                        const int pi0 = __shfl_up_sync(0xffffffffu, tp.idx[0], 1), pi1 = __shfl_up_sync(0xffffffffu, tp.idx[1], 1);
+                        const int pi2 = __shfl_up_sync(0xffffffffu, tp.idx[2], 1), pi3 = __shfl_up_sync(0xffffffffu, tp.idx[3], 1);
+                        const bool pdead = __shfl_up_sync(0xffffffffu, (int)dead, 1) != 0;
+                        const bool same = (lane > 0) & !pdead & (pi0 == tp.idx[0]) & (pi1 == tp.idx[1]) & (pi2 == tp.idx[2]) & (pi3 == tp.idx[3]);
+                        sts128(rowtab + row * 128 + sub * 32, make_uint4(dead ? 0xFFFFFFFFu : ((uint32_t)(tp.idx[0] * 32) | (same ? 1u : 0u)),
+                                                                          tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
                         sts128(rowtab + row * 128 + sub * 32 + 16, make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
                                                                                pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
 #pragma unroll
@@ -701,29 +711,42 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         for (int m = 1; m < 4; ++m)
                             mapbase[m] = reinterpret_cast<const uint4*>(P.mlp.pplane[m - 1] + (size_t)v * pl_hw * 256) + lane;
                         mbar_wait<kProdSleep>(BAR(G_FREE + slot), use ^ 1, P.err, 3);
+                        if (DBG) { long long t1 = clock64(); tp_gf_j[(v * 2 + h) % 8] += t1 - _t0; }
                         TLAP(tp_gwait);
                         const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + (lane & 15) * 16;
+                        // Each warp takes CONTIGUOUS rows: consecutive rows are neighbouring pixels of the 8x4 ray block at the same
+                        // sample index, which land in the same bilinear texel quad most of the time (a 64-point job touches ~4
+                        // distinct quads per plane, ~20 in the latent image).  A row whose quad equals the previous row's keeps the
+                        // 4 texels in registers instead of re-reading 2 KB through L1 (the gather's bound: 512 KB per job before).
+                        const int r_begin = (pw * kHalfPts) / kProducerWarps, r_end = ((pw + 1) * kHalfPts) / kProducerWarps;
+                        uint4 val[16];
 #pragma unroll 1
-                        for (int r = pw; r < kHalfPts; r += kProducerWarps) {
-                            uint4 val[16];
+                        for (int r = r_begin; r < r_end; ++r) {
+                            // the whole 128-byte row table in two batches of independent loads (one shared-memory round trip each,
+                            // the second hidden behind the texel loads) instead of eight dependent ones
+                            uint4 off[4];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) off[m] = lds128(rowtab + r * 128 + m * 32);
                             bool live[4];
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
-                                const uint4 off = lds128(rowtab + r * 128 + m * 32);
-                                live[m] = off.x != 0xFFFFFFFFu && !(P.ablate & 1);         // warp-uniform: out-of-range lookups contribute exact zeros
-                                if (live[m]) {
-                                    val[m * 4 + 0] = __ldg(mapbase[m] + off.x);
-                                    val[m * 4 + 1] = __ldg(mapbase[m] + off.y);
-                                    val[m * 4 + 2] = __ldg(mapbase[m] + off.z);
-                                    val[m * 4 + 3] = __ldg(mapbase[m] + off.w);
+                                live[m] = off[m].x != 0xFFFFFFFFu && !(P.ablate & 1);      // warp-uniform: out-of-range lookups contribute exact zeros
+                                const bool reuse = (off[m].x & 1u) && r > r_begin && !(P.ablate & 8);
+                                if (live[m] && !reuse) {
+                                    val[m * 4 + 0] = __ldg(mapbase[m] + (off[m].x & ~1u));
+                                    val[m * 4 + 1] = __ldg(mapbase[m] + off[m].y);
+                                    val[m * 4 + 2] = __ldg(mapbase[m] + off[m].z);
+                                    val[m * 4 + 3] = __ldg(mapbase[m] + off[m].w);
                                 }
                             }
+                            uint4 wq[4];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) wq[m] = lds128(rowtab + r * 128 + m * 32 + 16);
                             __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
                                 if (live[m]) {
-                                    const uint4 wq = lds128(rowtab + r * 128 + m * 32 + 16);
-                                    const uint32_t wv[4] = {wq.x, wq.y, wq.z, wq.w};
+                                    const uint32_t wv[4] = {wq[m].x, wq[m].y, wq[m].z, wq[m].w};
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
                                         const __half2 w = *reinterpret_cast<const __half2*>(&wv[k]);
@@ -739,14 +762,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                                               *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3)));
                         }
                         mbar_arrive_warp(BAR(G_READY + slot), lane);
+                        if (DBG) { long long t1 = clock64(); tp_ga_j[(v * 2 + h) % 8] += t1 - _t0; }
                         TLAP(tp_gather);
                     }
                 }
             }
         }
         if (DBG && P.dbg && ptid == 0) {
-            long long* d = P.dbg + (size_t)blockIdx.x * 16;
+            long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
             d[0] = tp_pts; d[1] = tp_encwait; d[2] = tp_geom; d[3] = tp_bar; d[4] = tp_gwait; d[5] = tp_gather;
+            for (int i = 0; i < 8; ++i) { d[24 + i] = tp_enc_j[i]; d[32 + i] = tp_gf_j[i]; d[48 + i] = tp_ga_j[i]; }
         }
     } else if (warp == 4) {
         // =====================================================================================
@@ -853,7 +878,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 wait_h(0, 16);
             }
             if (DBG && P.dbg && lane == 0) {
-                long long* d = P.dbg + (size_t)blockIdx.x * 16;
+                long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
                 d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue;
             }
         }
@@ -865,6 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         uint32_t ph_acc = 0, ph_head = 0, kcount = 0;     // bit b = parity of ACC_READY[b]
         long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
+        long long te_g_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, te_acc_l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         TSTART();
         const uint32_t hbase = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u;     // MN-major H: atom of 8 K rows, row c&7
         const uint32_t sH = sbase + SM_H, sBias = sbase + SM_BIAS;
@@ -883,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll 1
                         for (int bb = 0; bb < 2; ++bb) {
-                            if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); TLAP(te_gwait); }
+                            if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); if (DBG) { long long t1 = clock64(); te_g_j[(v * 2 + h) % 8] += t1 - _t0; } TLAP(te_gwait); }
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
                             uint32_t r[32];
                             if (l == 0) {
@@ -893,6 +919,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(gbase[(bb * 32 + i) * 128]);
                                 TLAP(te_work);
                                 mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20); ph_acc ^= 1u << bb;
+                                if (DBG) { long long t1 = clock64(); te_acc_l[bb] += t1 - _t0; }
                                 TLAP(te_accwait);
                                 tc_fence_after();
                                 tmem_ld32(lane_base + TM_D + bb * 32, r);
@@ -924,6 +951,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             } else {
                                 TLAP(te_work);
                                 mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
+                                if (DBG) { long long t1 = clock64(); te_acc_l[l * 2 + bb] += t1 - _t0; }
                                 TLAP(te_accwait);
                                 tc_fence_after();
                                 tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
@@ -1009,8 +1037,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             TLAP(te_head);
         }
         if (DBG && P.dbg && threadIdx.x == 0) {
-            long long* d = P.dbg + (size_t)blockIdx.x * 16;
+            long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
             d[9] = te_accwait; d[10] = te_gwait; d[11] = te_work; d[12] = te_head;
+            for (int i = 0; i < 8; ++i) { d[16 + i] = te_g_j[i]; d[40 + i] = te_acc_l[i]; }
         }
     }
     // ---- teardown ----

@@ -18,14 +18,14 @@ lib = L.load()
 with torch.no_grad():
     net.render_rays_test(rays, chunk=1024)
     lib.neo_tc_ablate(ablate)
-    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 64, dtype=torch.int64, device=dev)
     lib.neo_tc_debug(buf.data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.render_rays_test(rays, chunk=1024); e1.record(); torch.cuda.synchronize()
     lib.neo_tc_debug(None)
 ms = e0.elapsed_time(e1)
-b = buf.view(148, 16).double().cpu()
+b = buf.view(148, 64).double().cpu()
 names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P wait G_FREE", "P gather", "M wait ENC_READY", "M wait H_READY", "M issue",
          "E wait ACC", "E wait G", "E work", "E head"]
 # counters are overwritten by each of the 4 field launches: they hold the LAST launch (bg fine, N=193)
@@ -35,3 +35,8 @@ lib.neo_tc_ablate(0)
 print(f"ablate={ablate}: {n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
 for i, nm in enumerate(names):
     print(f"  {nm:18s} {b[:, i].mean() / halfjobs_per_cta:9.0f} cycles / half-job   (total {b[:, i].mean() / 1e6:8.2f} Mcyc)")
+
+jobs_per_bin = halfjobs_per_cta / 6
+for nm, off in (("E wait G by job (v*2+h)", 16), ("P wait ENC_FREE by job", 24), ("P wait G_FREE by job", 32), ("P gather by job", 48)):
+    print(f"  {nm:26s} " + " ".join(f"{b[:, off + i].mean() / jobs_per_bin:7.0f}" for i in range(6)))
+print("  E wait ACC by layer,block   " + " ".join(f"{b[:, 40 + i].mean() / halfjobs_per_cta:6.0f}" for i in range(8)))
