@@ -936,18 +936,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                     }
                                     *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                                 }
-                                // layer-3 accumulator (already W3enc.ENC + b3): += G3, in place in TMEM; after this nothing of the
-                                // gather slot is needed any more, so the producers get it back ~one job earlier
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(g3base[(bb * 32 + i) * 128]);
-                                tmem_ld32(lane_base + TM_D3 + bb * 32, r);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + gv[i]);
-                                tmem_st16(lane_base + TM_D3 + bb * 32, r);
-                                tmem_st16(lane_base + TM_D3 + bb * 32 + 16, r + 16);
-                                tc_wait_st();
-                                if (bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
                             } else {
                                 TLAP(te_work);
                                 mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
@@ -971,6 +959,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             tc_fence_before();
                             fence_proxy_async();
                             mbar_arrive_warp(BAR(H_READY + bb), lane);
+                            if (l == 0) {
+                                // (after the arrive: the layer-1 MMA of this block is already running while this happens)
+                                float gv[32];
+                                // layer-3 accumulator (already W3enc.ENC + b3): += G3, in place in TMEM; after this nothing of the
+                                // gather slot is needed any more, so the producers get it back ~one job earlier
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(g3base[(bb * 32 + i) * 128]);
+                                tmem_ld32(lane_base + TM_D3 + bb * 32, r);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + gv[i]);
+                                tmem_st16(lane_base + TM_D3 + bb * 32, r);
+                                tmem_st16(lane_base + TM_D3 + bb * 32 + 16, r + 16);
+                                tc_wait_st();
+                                if (bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
+                            }
                         }
                     }
                 }
