@@ -253,6 +253,9 @@ int neo_profile_read(float* field_ms, int* n_field, unsigned long long* launches
  * computed with fp16 operands / fp32 accumulation. */
 int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1, float* out2, float* out3, float* out4,
                     void* stream);
+/* Self-test of the transpose-accumulate MMA that adds gathered features into the trunk accumulators (identity A operand,
+ * no-swizzle K-major): outa / outb (128,128) = X^T under the two readings of the descriptor's LBO/SBO fields. */
+int neo_tc_selftest_transpose(const float* X, float* outa, float* outb, void* stream);
 
 /* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 16)
  * int64; NULL disables.  Roles and slots are documented in csrc/field_tc.cu. */

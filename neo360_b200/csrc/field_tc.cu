@@ -43,7 +43,8 @@ constexpr uint32_t SM_PTS = 207872;       // per-tile cache: 128 rows x 48 B (wo
 constexpr uint32_t SM_VIEWS = 214016;     // kMaxViews x 64 B source-camera transforms
 constexpr uint32_t SM_BAR = 214528;
 constexpr uint32_t SM_SEL = 215040;       // 32 x 128 B one-hot selector tile (SW128): B operand of the bias MMA, k-step l selects layer l
-constexpr uint32_t SM_TOTAL = 219136;
+constexpr uint32_t SM_IDENT = 219136;     // shifted-identity tile (7680 B, no swizzle): A operand of the transpose-accumulate MMA
+constexpr uint32_t SM_TOTAL = 226816;
 constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB = 8192;
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 
@@ -187,6 +188,33 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
+}
+// K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 B stored as 128 contiguous bytes; LBO = byte stride between the
+// core matrices of one 8-row group along K, SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// Shifted-identity tile (A operand of the "transpose-accumulate" MMA that adds the gathered features G[point][channel] into the
+// accumulator D[channel][point]): 240 rows x 16 k, zero except a 16x16 identity at rows 112..127.  The A operand of k-step s is
+// the 128-row window starting at row 112 - 16 s, whose identity block then sits at rows 16 s .. 16 s + 15.
+constexpr uint32_t IDENT_LBO = 128, IDENT_SBO = 256, IDENT_BYTES = 30 * 256;
+__device__ __forceinline__ void ident_fill(unsigned char* tile, int tid, int nthreads) {
+    for (int i = tid; i < (int)IDENT_BYTES / 16; i += nthreads) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void ident_ones(unsigned char* tile, int tid) {     // call after ident_fill + barrier, tid 0..15
+    if (tid < 16) {
+        const int r = 112 + tid, k = tid;
+        *reinterpret_cast<__half*>(tile + (r >> 3) * IDENT_SBO + (k >> 3) * IDENT_LBO + (r & 7) * 16 + (k & 7) * 2) = __float2half_rn(1.0f);
+    }
+}
+__device__ __forceinline__ uint64_t desc_ident(uint32_t tile_saddr, int ks, bool swap = false) {
+    const uint32_t a = tile_saddr + (uint32_t)(14 - 2 * ks) * IDENT_SBO;
+    return swap ? desc_nosw(a, IDENT_SBO, IDENT_LBO) : desc_nosw(a, IDENT_LBO, IDENT_SBO);
 }
 // MN-major, 128-byte-swizzled operand: 64 consecutive M/N elements (128 B) per K row, 8 K rows per 1024-B atom;
 // SBO = byte stride between 8-K-row atoms, LBO = byte stride between 64-element groups along M/N.
@@ -349,11 +377,11 @@ __global__ void wimg_kernel(NeoMLPParams p, int enc_dim, int KE, uint32_t* __res
     for (int h = 0; h < 2; ++h) {
         int k = 2 * j + h;
         float x;
-        if (k < KE) x = (k < enc_dim) ? p.w0[(size_t)n * in_dim + k] : 0.f;
+        if (k < KE) x = (k < enc_dim) ? p.w0[(size_t)n * in_dim + k] : (k == enc_dim ? p.b0[n] : 0.f);      // bias on the constant-one input
         else if (k < KE + 128) x = p.w1[n * 128 + (k - KE)];
         else if (k < KE + 256) x = p.w2[n * 128 + (k - KE - 128)];
         else if (k < KE + 384) x = p.w3[(size_t)n * (128 + in_dim) + (k - KE - 256)];
-        else { int kk = k - KE - 384; x = (kk < enc_dim) ? p.w3[(size_t)n * (128 + in_dim) + 128 + kk] : 0.f; }
+        else { int kk = k - KE - 384; x = (kk < enc_dim) ? p.w3[(size_t)n * (128 + in_dim) + 128 + kk] : (kk == enc_dim ? p.b3[n] : 0.f); }
         v[h] = x;
     }
     out[idx] = pack_h2(v[0], v[1]);
@@ -450,7 +478,8 @@ __device__ __forceinline__ uint4 enc_chunk(int c, const float* x) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int e = c * 8 + i;
-        if (e >= ENC) v[i] = 0.f;
+        if (e == ENC) v[i] = 1.0f;            // constant-one input: column ENC of W0enc / W3enc holds the layer bias
+        else if (e > ENC) v[i] = 0.f;
         else if (e < ICH) v[i] = x[e];
         else {
             constexpr int HALF = ICH * kPosDeg;
@@ -483,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             mbar_init(BAR(ENC_READY + s), kProducerWarps);        // one elected arrival per warp
             mbar_init(BAR(ENC_FREE + s), 1);
             mbar_init(BAR(G_READY + s), kProducerWarps);
-            mbar_init(BAR(G_FREE + s), 4);
+            mbar_init(BAR(G_FREE + s), 1);                         // tcgen05.commit after the layer-0 MMAs that read the slot
         }
         mbar_init(BAR(ACC_READY), 1);
         mbar_init(BAR(ACC_READY + 1), 1);
@@ -551,6 +580,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             }
             *reinterpret_cast<uint4*>(sgen + SM_SEL + row * 128 + ((chunk ^ (row & 7)) << 4)) = z;
         }
+        ident_fill(sgen + SM_IDENT, ptid0, kProducerWarps * 32);
+        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
+        ident_ones(sgen + SM_IDENT, ptid0);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -713,7 +745,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         mbar_wait<kProdSleep>(BAR(G_FREE + slot), use ^ 1, P.err, 3);
                         if (DBG) { long long t1 = clock64(); tp_gf_j[(v * 2 + h) % 8] += t1 - _t0; }
                         TLAP(tp_gwait);
-                        const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + (lane & 15) * 16;
+                        // G0 / G3 tiles are B operands of the transpose-accumulate MMA: SW128 K-major, 2 slabs of 64 rows x 128 B (64 channels)
+                        const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + ((lane & 15) >> 3) * 8192;
+                        const uint32_t gchunk = lane & 7;
                         // Each warp takes CONTIGUOUS rows: consecutive rows are neighbouring pixels of the 8x4 ray block at the same
                         // sample index, which land in the same bilinear texel quad most of the time (a 64-point job touches ~4
                         // distinct quads per plane, ~20 in the latent image).  A row whose quad equals the previous row's keeps the
@@ -758,9 +792,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                     }
                                 }
                             }
-                            sts128(gdst + r * 256, make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
+                            sts128(gdst + r * 128 + ((gchunk ^ (uint32_t)(r & 7)) << 4), make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
                                                               *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3)));
                         }
+                        fence_proxy_async();                   // the tensor core (async proxy) reads the G tiles
                         mbar_arrive_warp(BAR(G_READY + slot), lane);
                         if (DBG) { long long t1 = clock64(); tp_ga_j[(v * 2 + h) % 8] += t1 - _t0; }
                         TLAP(tp_gather);
@@ -780,15 +815,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         {
             // all 32 lanes run this loop (waits included); MMAs/commits are issued by one elected lane
             uint32_t ph_h = 0, kcount = 0;      // bit b = parity of H_READY[b]
-            long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0;
+            long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0, tm_gwait = 0;
             TSTART();
             // ENC (K-major, written by row owners) and H (MN-major = point-contiguous, written by neuron owners as 16-byte vectors)
             const uint32_t id_blk = idesc_f16(128, 32), id_blk_mn = idesc_f16(128, 32, 0, 1), id_head = idesc_f16(128, 80, 1, 0),
-                           id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16);
+                           id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16), id_half = idesc_f16(128, 64);
             const uint32_t dD = tmem + TM_D, dD3 = tmem + TM_D3, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
-            const uint32_t aB = tmem + TM_BIAS;
+            const uint32_t aB = tmem + TM_BIAS, sIDENT = sbase + SM_IDENT;
             const uint64_t dSEL = desc_sw128(sbase + SM_SEL);          // + 2 l: k-step l = one-hot of layer l
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
             // descriptor of k-step ks = base descriptor + ((ks>>2)*slab + (ks&3)*32) / 16 in the start-address field
@@ -811,20 +846,37 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         mbar_wait(BAR(ENC_READY + slot), use, P.err, 10);
                         TLAP(tm_encwait);
                         tc_fence_after();
-                        // L0 of both 32-point blocks: D[:, 32b:32b+32] = W0enc . ENC[rows 32b..]^T
+                        // Layer 0 of the whole 64-point half (N = 64): D = W0enc . ENC^T (b0 rides on the constant-one input column).
+                        // Gathered features: D += G0^T through the transpose-accumulate MMA (A = shifted identity), so the epilogue
+                        // warps never touch the gather tiles.
                         if (elect_one()) {
-                            for (int bb = 0; bb < 2; ++bb) {
 #pragma unroll
-                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD + 32 * bb, aW0 + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
-                                // skip connection of layer 3 (model.py:142-146): its encoding part is accumulated NOW into a second
-                                // accumulator, so the ENC slot is released after layer 0 instead of after layer 3
+                            for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW0 + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
+                        }
+                        __syncwarp();
+                        TLAP(tm_issue);
+                        mbar_wait(BAR(G_READY + slot), use, P.err, 12);
+                        TLAP(tm_gwait);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t dG0 = desc_sw128(sbase + SM_G0 + slot * SLOT_G), dG3 = desc_sw128(sbase + SM_G3 + slot * SLOT_G);
+                            if (!(P.ablate & 4)) {
 #pragma unroll
-                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3 + 32 * bb, aW3e + ks * 8, dk(dENC[bb], ks, SLAB_ENC), id_blk, ks > 0);
-                                mma_ts(dD + 32 * bb, aB, dSEL, id_blk, 1);              // + b0
-                                mma_ts(dD3 + 32 * bb, aB, dSEL + 6, id_blk, 1);         // + b3
-                                tc_commit(BAR(ACC_READY + bb));
+                                for (int ks = 0; ks < 8; ++ks) mma_ss(dD, desc_ident(sIDENT, ks), dk(dG0, ks, 8192), id_half, 1);
+                            }
+                            tc_commit(BAR(ACC_READY));
+                            tc_commit(BAR(ACC_READY + 1));
+                            // Skip connection of layer 3 (model.py:142-146), off the critical path: its encoding and gathered parts
+                            // (and b3) are accumulated NOW into a second accumulator D3, on which layer 3 later accumulates W3h . h2 --
+                            // so the ENC and gather slots go back to the producers after layer 0 instead of after layer 3.
+#pragma unroll
+                            for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3, aW3e + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
+                            if (!(P.ablate & 4)) {
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks) mma_ss(dD3, desc_ident(sIDENT, ks), dk(dG3, ks, 8192), id_half, 1);
                             }
                             tc_commit(BAR(ENC_FREE + slot));
+                            tc_commit(BAR(G_FREE + slot));
                         }
                         __syncwarp();
                         for (int l = 1; l <= 3; ++l) {
@@ -835,7 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
 #pragma unroll
                                     for (int ks = 0; ks < 8; ++ks)
                                         mma_ts((l == 3 ? dD3 : dD) + 32 * bb, aW + ks * 8, dHb[bb] + (uint64_t)(ks * (2048 >> 4)), id_blk_mn, (l == 3) || ks > 0);
-                                    if (l < 3) mma_ts(dD + 32 * bb, aB, dSEL + (uint64_t)(2 * l), id_blk, 1);     // + b_l
+                                    if (l < 3) mma_ts(dD + 32 * bb, aB, dSEL + (uint64_t)(2 * l), id_blk, 1);     // + b_l  (b0, b3: ENC constant column)
                                     tc_commit(BAR(ACC_READY + bb));
                                 }
                                 __syncwarp();
@@ -879,7 +931,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             }
             if (DBG && P.dbg && lane == 0) {
                 long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
-                d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue;
+                d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue; d[13] = tm_gwait;
             }
         }
     } else {
@@ -902,79 +954,34 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     const uint32_t sHh = sH + h * 16384;
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
-                        // biases arrive through the bias MMA; layer 3's gathered part was folded into its accumulator during the
-                        // layer-0 epilogue (below), so layers 1-3 are: TMEM load -> fp16 pack -> packed ReLU -> 4 x 16-byte stores
-                        const __half* gbase = reinterpret_cast<const __half*>(sgen + SM_G0 + slot * SLOT_G) + c;    // G0[slot][0][c]
-                        const __half* g3base = reinterpret_cast<const __half*>(sgen + SM_G3 + slot * SLOT_G) + c;   // G3[slot][0][c]
+                        // biases arrive through the bias MMA and the gathered features through the transpose-accumulate MMA, so every
+                        // layer is: TMEM load -> fp16 pack -> packed ReLU -> 4 x 16-byte stores of this neuron's K row
                         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll 1
                         for (int bb = 0; bb < 2; ++bb) {
-                            if (l == 0 && bb == 0) { TLAP(te_work); mbar_wait(BAR(G_READY + slot), use, P.err, 24); if (DBG) { long long t1 = clock64(); te_g_j[(v * 2 + h) % 8] += t1 - _t0; } TLAP(te_gwait); }
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
                             uint32_t r[32];
-                            if (l == 0) {
-                                // gathered features of this block first (plain shared loads, all in flight), then the accumulator
-                                float gv[32];
+                            TLAP(te_work);
+                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
+                            if (DBG) { long long t1 = clock64(); te_acc_l[l * 2 + bb] += t1 - _t0; }
+                            TLAP(te_accwait);
+                            tc_fence_after();
+                            tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
+                            tc_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(gbase[(bb * 32 + i) * 128]);
-                                TLAP(te_work);
-                                mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20); ph_acc ^= 1u << bb;
-                                if (DBG) { long long t1 = clock64(); te_acc_l[bb] += t1 - _t0; }
-                                TLAP(te_accwait);
-                                tc_fence_after();
-                                tmem_ld32(lane_base + TM_D + bb * 32, r);
-                                tc_wait_ld();
+                            for (int j4 = 0; j4 < 4; ++j4) {          // 8 consecutive points = one 16-byte vector of this neuron's K row
+                                uint32_t w[4];
 #pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) {          // 8 consecutive points = one 16-byte vector of this neuron's K row
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        const uint32_t pk = pack_h2(__uint_as_float(r[8 * j4 + 2 * i]) + gv[8 * j4 + 2 * i],
-                                                                    __uint_as_float(r[8 * j4 + 2 * i + 1]) + gv[8 * j4 + 2 * i + 1]);
-                                        const __half2 hv = __hmax2(*reinterpret_cast<const __half2*>(&pk), zero2);
-                                        w[i] = *reinterpret_cast<const uint32_t*>(&hv);
-                                    }
-                                    *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t pk = pack_h2(__uint_as_float(r[8 * j4 + 2 * i]), __uint_as_float(r[8 * j4 + 2 * i + 1]));
+                                    const __half2 hv = __hmax2(*reinterpret_cast<const __half2*>(&pk), zero2);
+                                    w[i] = *reinterpret_cast<const uint32_t*>(&hv);
                                 }
-                            } else {
-                                TLAP(te_work);
-                                mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
-                                if (DBG) { long long t1 = clock64(); te_acc_l[l * 2 + bb] += t1 - _t0; }
-                                TLAP(te_accwait);
-                                tc_fence_after();
-                                tmem_ld32(lane_base + (l == 3 ? TM_D3 : TM_D) + bb * 32, r);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) {
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        const uint32_t pk = pack_h2(__uint_as_float(r[8 * j4 + 2 * i]), __uint_as_float(r[8 * j4 + 2 * i + 1]));
-                                        const __half2 hv = __hmax2(*reinterpret_cast<const __half2*>(&pk), zero2);
-                                        w[i] = *reinterpret_cast<const uint32_t*>(&hv);
-                                    }
-                                    *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                                }
+                                *reinterpret_cast<uint4*>(hp + ((((bb << 2) + j4) ^ (c & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                             }
                             tc_fence_before();
                             fence_proxy_async();
                             mbar_arrive_warp(BAR(H_READY + bb), lane);
-                            if (l == 0) {
-                                // (after the arrive: the layer-1 MMA of this block is already running while this happens)
-                                float gv[32];
-                                // layer-3 accumulator (already W3enc.ENC + b3): += G3, in place in TMEM; after this nothing of the
-                                // gather slot is needed any more, so the producers get it back ~one job earlier
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) gv[i] = (P.ablate & 4) ? 0.f : __half2float(g3base[(bb * 32 + i) * 128]);
-                                tmem_ld32(lane_base + TM_D3 + bb * 32, r);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + gv[i]);
-                                tmem_st16(lane_base + TM_D3 + bb * 32, r);
-                                tmem_st16(lane_base + TM_D3 + bb * 32 + 16, r + 16);
-                                tc_wait_st();
-                                if (bb == 1) mbar_arrive_warp(BAR(G_FREE + slot), lane);
-                            }
                         }
                     }
                 }
@@ -1147,6 +1154,54 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// self-test of the transpose-accumulate MMA: outa[n][p] = outb[n][p] = X[p][n] (fp16-rounded), X (128 points, 128 channels) staged as the
+// SW128 K-major tile the producers write; outa uses (LBO, SBO) = (K stride, 8-row-group stride), outb the swapped reading of the
+// descriptor fields (exactly one of them is right; the test pins which, the kernel uses that one)
+__global__ void __launch_bounds__(128, 1) selftest_transpose_kernel(const float* __restrict__ X, float* __restrict__ outa,
+                                                                    float* __restrict__ outb, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sX = sbase, sI = sbase + 32768, bar = sbase + 32768 + 8192;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + 32768 + 8192 + 16);
+    const int warp = threadIdx.x >> 5, c = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(sbase + 32768 + 8192 + 16, 512);
+    __half* xs = reinterpret_cast<__half*>(sgen);
+    for (int e = threadIdx.x; e < 128 * 128; e += 128) xs[sw128_off(e / 128, e % 128, 128) / 2] = __float2half_rn(X[e]);
+    ident_fill(sgen + 32768, threadIdx.x, 128);
+    __syncthreads();
+    ident_ones(sgen + 32768, threadIdx.x);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    if (threadIdx.x == 0) {
+        for (int var = 0; var < 2; ++var)
+            for (int blk = 0; blk < 4; ++blk)
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ss(tmem + 128 * var + 32 * blk, desc_ident(sI, ks, var == 1),
+                           desc_sw128(sX + (ks >> 2) * 16384 + blk * 32 * 128 + (ks & 3) * 32), idesc_f16(128, 32), ks > 0);
+        tc_commit(bar);
+    }
+    mbar_wait(bar, 0, err, 97);
+    tc_fence_after();
+    for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) outa[c * 128 + cb * 32 + i] = __uint_as_float(r[i]);
+        tmem_ld32(lane_base + 128 + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) outb[c * 128 + cb * 32 + i] = __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -1269,6 +1324,14 @@ extern "C" int neo_tc_selftest(const float* X, const float* W, const float* Wn, 
 // Debug: cycle accounting of the TC field kernel.  buf = device array of 148*16 int64 (zeroed by the caller) or NULL to disable.
 // Per CTA: [0] pts [1] wait ENC_FREE [2] geometry [3] producer bar [4] wait G_FREE [5] gather | [6] MMA wait ENC_READY
 // [7] MMA wait H_READY [8] MMA issue | [9] epi wait ACC [10] epi wait G [11] epi work [12] epi head
+extern "C" int neo_tc_selftest_transpose(const float* X, float* outa, float* outb, void* stream) {
+    using namespace neo;
+    const size_t smem = 32768 + 8192 + 64 + 1024;
+    NEO_CUDA(cudaFuncSetAttribute(tc::selftest_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::selftest_transpose_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, outa, outb, nullptr);
+    NEO_LAUNCH_CHECK("selftest_transpose_kernel");
+    return NEO_OK;
+}
 extern "C" int neo_tc_debug(long long* buf) { neo::g_dbg = buf; return NEO_OK; }
 // Debug: sensitivity experiments -- the kernel skips parts of its work (results become wrong!): see Params::ablate.
 extern "C" int neo_tc_ablate(int mask) { neo::g_ablate = mask; return NEO_OK; }

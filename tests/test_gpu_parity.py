@@ -274,6 +274,22 @@ def test_tc_primitives_selftest(cuda):
     assert md(o4, Xh @ Wnh.T) < 1e-3          # MN-major A operand, M=128 as two 64-point groups
 
 
+def test_tc_selftest_transpose(cuda):
+    """Transpose-accumulate MMA (identity A operand in a no-swizzle K-major tile, gathered features as the SW128 K-major B
+    operand): exact transposition of the fp16-rounded input.  `outa` is the descriptor reading the kernel uses."""
+    from neo360_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(128, 128, generator=g).to(cuda)
+    oa = torch.zeros(128, 128, device=cuda)
+    ob = torch.zeros(128, 128, device=cuda)
+    L.check(lib.neo_tc_selftest_transpose(L.ptr(X), L.ptr(oa), L.ptr(ob), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = X.half().float().T
+    print("transpose MMA: (LBO=K stride, SBO=row-group stride) err", md(oa, ref), " swapped err", md(ob, ref))
+    assert md(oa, ref) == 0.0
+
+
 def test_field_eval_tc_vs_oracle(cuda):
     """TC field (fp16 operands, pre-projected features, folded head) against the oracle on identical t-values.
     Stated tolerance: |rgb| 2e-2, sigma 2e-2 + 2% (fp16 operand rounding through a 6-layer gained MLP)."""

@@ -27,7 +27,7 @@ with torch.no_grad():
 ms = e0.elapsed_time(e1)
 b = buf.view(148, 64).double().cpu()
 names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P wait G_FREE", "P gather", "M wait ENC_READY", "M wait H_READY", "M issue",
-         "E wait ACC", "E wait G", "E work", "E head"]
+         "E wait ACC", "E wait G", "E work", "E head", "M wait G_READY"]
 # counters are overwritten by each of the 4 field launches: they hold the LAST launch (bg fine, N=193)
 tiles = ((n + 31) // 32) * ((193 + 3) // 4)
 halfjobs_per_cta = tiles * 6 / 148
