@@ -604,6 +604,30 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         PtsRow* pts = reinterpret_cast<PtsRow*>(sgen + SM_PTS);
         const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
         const size_t lat_hw = (size_t)P.sc.lat_h * P.sc.lat_w, pl_hw = (size_t)P.sc.plane_h * P.sc.plane_w;
+        // View-independent world points of the 64 rows of half `hh` of tile `tile` (one thread per row).  The two dependent
+        // global round trips (ray order -> ray, far, t) are hidden: producer warps 8-9, idle while warps 0-7 do the per-view
+        // geometry, compute half 1 of the current tile during job (v=0,h=0) and half 0 of the NEXT tile during the last job.
+        auto pts_compute = [&](int tile, int hh, int th) {
+            const int g2 = tile / P.sg, q2 = tile % P.sg;
+            const int n = hh * kHalfPts + th, rl = n & 31, sl = n >> 5;
+            const int slot_r = min(g2 * kTileRays + rl, P.n_rays - 1);
+            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
+            const int s = min(q2 * kTileSamples + sl, N - 1);
+            const float fr = P.far[rid];
+            const float tv = P.tvals[(long long)rid * N + s];
+            RayFast rg;
+            ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
+            PtsRow pr;
+            pr.tv = tv;
+            if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
+            else {
+                for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
+            }
+            pts[n] = pr;
+        };
+        if (ptid < kHalfPts && (int)blockIdx.x < P.n_tiles) pts_compute(blockIdx.x, 0, ptid);
+        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
+        TLAP(tp_pts);
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
@@ -611,28 +635,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
                     const uint32_t rowtab = sbase + SM_ROWTAB + slot * SLOT_TAB;
                     const uint32_t encb = sbase + SM_ENC + slot * SLOT_ENC;
-                    if (v == 0) {
-                        // ---- per-tile, view-independent world points of rows 64h..64h+63 (one thread per row) ----
-                        if (ptid < kHalfPts) {
-                            const int n = h * kHalfPts + ptid, rl = n & 31, sl = n >> 5;
-                            const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
-                            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
-                            const int s = min(q * kTileSamples + sl, N - 1);
-                            const float fr = P.far[rid];
-                            const float tv = P.tvals[(long long)rid * N + s];
-                            RayFast rg;
-                            ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
-                            PtsRow pr;
-                            pr.tv = tv;
-                            if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
-                            else {
-                                for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
-                            }
-                            pts[n] = pr;
-                        }
-                        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));    // PTS visible to all producer threads
-                        TLAP(tp_pts);
-                    }
                     if (v == nv - 1) {
                         // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360);
                         //      written with the LAST view so the previous tile's head MMA has long released the DIR tile ----
@@ -732,6 +734,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     }
                     fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
                     mbar_arrive_warp(BAR(ENC_READY + slot), lane);
+                    if (ptid >= 256 && ptid < 256 + kHalfPts) {
+                        if (v == 0 && h == 0) pts_compute(t, 1, ptid - 256);
+                        else if (v == nv - 1 && h == 1 && t + (int)gridDim.x < P.n_tiles) pts_compute(t + gridDim.x, 0, ptid - 256);
+                    }
                     TLAP(tp_geom);
                     asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB[slot] complete
                     TLAP(tp_bar);
