@@ -365,6 +365,33 @@ __global__ void __launch_bounds__(256) preproject_kernel(const float* __restrict
     }
 }
 
+// ---- positional encoding of the camera-frame point (helper.py:121-125), tensor-core operand layout ----
+// The MMA does not care about the ORDER of the K columns as long as W0enc / W3enc use the same one (wimg_kernel), so the columns
+// are grouped per coordinate: [x, sin(2^0 x) .. sin(2^9 x), cos(2^0 x) .. cos(2^9 x)] -- 21 columns per coordinate, stride 21
+// (3 coordinates + the constant-one column 63 = 64 = KE) or stride 24 (4 coordinates, column 21 = constant one, KE = 96).
+// One thread produces KE/4 consecutive columns and needs at most two coordinates, whose 20 sines/cosines come from ONE
+// sin/cos evaluation and the double-angle recurrence instead of 20 range-reduced evaluations.
+struct EncCol { int kind, cc, lvl; };          // kind 0: zero, 1: constant one, 2: x, 3: sin level, 4: cos level
+template <int ICH>
+__host__ __device__ constexpr EncCol enc_col(int col) {
+    constexpr int STRIDE = (ICH == 3) ? 21 : 24;
+    const int cc = col / STRIDE, j = col % STRIDE;
+    if (ICH == 3 && col == 63) return {1, 0, 0};
+    if (ICH == 4 && col == 21) return {1, 0, 0};
+    if (cc >= ICH || j >= 21) return {0, 0, 0};
+    if (j == 0) return {2, cc, 0};
+    if (j <= 10) return {3, cc, j - 1};
+    return {4, cc, j - 11};
+}
+// index of an encoding column in the reference's ordering (x, then per level all coordinates' sines, then the cosines); -1: none
+template <int ICH>
+__host__ __device__ constexpr int enc_col_ref_index(int col) {
+    const EncCol e = enc_col<ICH>(col);
+    if (e.kind == 2) return e.cc;
+    if (e.kind == 3) return ICH + e.lvl * ICH + e.cc;
+    if (e.kind == 4) return ICH + kPosDeg * ICH + e.lvl * ICH + e.cc;
+    return -1;
+}
 // TMEM weight image: word j of neuron n = fp16(Wcat[n][2j]) | fp16(Wcat[n][2j+1]) << 16,
 // Wcat = [W0enc (KE) | W1 (128) | W2 (128) | W3h (128) | W3enc (KE)]
 __global__ void wimg_kernel(NeoMLPParams p, int enc_dim, int KE, uint32_t* __restrict__ out) {
@@ -373,15 +400,23 @@ __global__ void wimg_kernel(NeoMLPParams p, int enc_dim, int KE, uint32_t* __res
     if (idx >= (KW / 2) * 128) return;
     int j = idx / 128, n = idx % 128;
     const int in_dim = enc_dim + kLocalCh + kWorldCh;
+    const bool bg = (KE == 96);
+    // encoding column `col` of the kernel's operand layout (enc_col<>): reference column, bias (constant-one column) or zero
+    auto enc_w = [&](const float* w, size_t stride, size_t off0, const float* bias, int col) -> float {
+        const EncCol e = bg ? enc_col<4>(col) : enc_col<3>(col);
+        if (e.kind == 1) return bias[n];
+        const int ref = bg ? enc_col_ref_index<4>(col) : enc_col_ref_index<3>(col);
+        return ref >= 0 ? w[(size_t)n * stride + off0 + ref] : 0.f;
+    };
     float v[2];
     for (int h = 0; h < 2; ++h) {
         int k = 2 * j + h;
         float x;
-        if (k < KE) x = (k < enc_dim) ? p.w0[(size_t)n * in_dim + k] : (k == enc_dim ? p.b0[n] : 0.f);      // bias on the constant-one input
+        if (k < KE) x = enc_w(p.w0, in_dim, 0, p.b0, k);
         else if (k < KE + 128) x = p.w1[n * 128 + (k - KE)];
         else if (k < KE + 256) x = p.w2[n * 128 + (k - KE - 128)];
         else if (k < KE + 384) x = p.w3[(size_t)n * (128 + in_dim) + (k - KE - 256)];
-        else { int kk = k - KE - 384; x = (kk < enc_dim) ? p.w3[(size_t)n * (128 + in_dim) + 128 + kk] : (kk == enc_dim ? p.b3[n] : 0.f); }
+        else x = enc_w(p.w3, 128 + in_dim, 128, p.b3, k - KE - 384);
         v[h] = x;
     }
     out[idx] = pack_h2(v[0], v[1]);
@@ -471,27 +506,40 @@ struct PtsRow {        // 48 bytes: view-independent per-row data, computed once
 };
 
 // one positional-encoding chunk (8 consecutive K elements) of row `x`
-template <int ICH>
-__device__ __forceinline__ uint4 enc_chunk(int c, const float* x) {
-    constexpr int ENC = ICH * 21;
-    float v[8];
+template <int ICH, int SUB>
+__device__ __forceinline__ void enc_cols(const float* x, uint32_t encb, int row, bool zero) {
+    constexpr int KE = (ICH == 3) ? 64 : 96, CP = KE / 4, C0 = SUB * CP;
+    constexpr int STRIDE = (ICH == 3) ? 21 : 24;
+    constexpr int cA = (C0 / STRIDE < ICH) ? C0 / STRIDE : ICH - 1;
+    constexpr int cB = ((C0 + CP - 1) / STRIDE < ICH) ? (C0 + CP - 1) / STRIDE : ICH - 1;
+    float sn[2][kPosDeg], cs[2][kPosDeg];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int e = c * 8 + i;
-        if (e == ENC) v[i] = 1.0f;            // constant-one input: column ENC of W0enc / W3enc holds the layer bias
-        else if (e > ENC) v[i] = 0.f;
-        else if (e < ICH) v[i] = x[e];
-        else {
-            constexpr int HALF = ICH * kPosDeg;
-            const int q0 = e - ICH;
-            const bool shifted = q0 >= HALF;
-            const int q = shifted ? q0 - HALF : q0;
-            const int k = q / ICH, cc = q % ICH;
-            const float xb = x[cc] * (float)(1 << k);
-            v[i] = __sinf(shifted ? xb + 1.57079637f : xb);     // helper.py:124
+    for (int w = 0; w < 2; ++w) {
+        if (w == 1 && cB == cA) break;
+        const float xv = x[w == 0 ? cA : cB];
+        float s = __sinf(xv), c = __cosf(xv);
+#pragma unroll
+        for (int k = 0; k < kPosDeg; ++k) {
+            sn[w][k] = s; cs[w][k] = c;
+            const float s2 = 2.f * s * c, c2 = fmaf(c, c, -s * s);
+            s = s2; c = c2;
         }
     }
-    return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    float v[CP];
+#pragma unroll
+    for (int i = 0; i < CP; ++i) {
+        const EncCol e = enc_col<ICH>(C0 + i);
+        const int w = (e.cc == cA) ? 0 : 1;
+        v[i] = (e.kind == 1) ? 1.0f : (e.kind == 2) ? x[e.cc] : (e.kind == 3) ? sn[w][e.lvl] : (e.kind == 4) ? cs[w][e.lvl] : 0.f;
+        if (zero) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < CP / 8; ++j) {
+        const int c = C0 / 8 + j;
+        sts128(encb + (c >> 3) * SLAB_ENC + row * 128 + (((c & 7) ^ (row & 7)) << 4),
+               make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                          pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7])));
+    }
 }
 
 template <int ICH, bool DBG>
@@ -724,11 +772,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                                                           tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
                         sts128(rowtab + row * 128 + sub * 32 + 16, make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
                                                                                pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
-#pragma unroll
-                        for (int c = 0; c < KE / 8; ++c) {
-                            if ((c & 3) == sub) {
-                                const uint4 pk = (P.ablate & 2) ? make_uint4(0u, 0u, 0u, 0u) : enc_chunk<ICH>(c, ce);
-                                sts128(encb + (c >> 3) * SLAB_ENC + row * 128 + (((c & 7) ^ (row & 7)) << 4), pk);
+                        {
+                            const bool zero = (P.ablate & 2) != 0;
+                            switch (sub) {                  // warp-uniform
+                                case 0: enc_cols<ICH, 0>(ce, encb, row, zero); break;
+                                case 1: enc_cols<ICH, 1>(ce, encb, row, zero); break;
+                                case 2: enc_cols<ICH, 2>(ce, encb, row, zero); break;
+                                default: enc_cols<ICH, 3>(ce, encb, row, zero); break;
                             }
                         }
                     }
