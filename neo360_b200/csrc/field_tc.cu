@@ -26,7 +26,6 @@ constexpr int kProducerWarp0 = 5;
 constexpr int kProducerWarps = 11;
 constexpr int kTileRays = 32;
 constexpr int kTileSamples = 4;
-constexpr int kTilePts = 128;
 constexpr int kHalfPts = 64;          // producer->consumer unit: half a tile (32 rays x 2 samples) x 1 view
 
 // ---- shared memory map (bytes; UMMA tiles 1024-aligned) ----
@@ -996,7 +995,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         // =====================================================================================
         const int c = warp * 32 + lane;                 // neuron (trunk) / point row (head)
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ph_acc = 0, ph_head = 0, kcount = 0;     // bit b = parity of ACC_READY[b]
+        uint32_t ph_acc = 0, ph_head = 0;     // bit b = parity of ACC_READY[b]
         long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
         long long te_g_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, te_acc_l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         TSTART();
@@ -1005,8 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
-                for (int h = 0; h < 2; ++h, ++kcount) {
-                    const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
+                for (int h = 0; h < 2; ++h) {
                     const uint32_t sHh = sH + h * 16384;
 #pragma unroll 1
                     for (int l = 0; l < 4; ++l) {
@@ -1129,7 +1127,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sX = sbase, sWn = sbase + 32768, sXmn = sbase + 53248, bar = sbase + 86016;
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + 86016 + 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = threadIdx.x;
+    const int warp = threadIdx.x >> 5, c = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc(sbase + 86016 + 16, 512);
     __half* xs = reinterpret_cast<__half*>(sgen);
