@@ -57,7 +57,8 @@ constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   
 // slot-indexed barriers come in pairs (slot 0, slot 1)
 // ACC_READY / H_READY are indexed by the 32-point block (0/1) of the half-job: the two blocks ping-pong between the
 // tensor core and the epilogue warps, so MMA latency hides behind the other block's epilogue.
-enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY = 10, HEAD_READY = 12, DIR_FREE, NUM_BARS };
+enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY = 10, HEAD_READY = 12, DIR_FREE,
+           Q_READY, CH_READY, HEAD_DONE, NUM_BARS };      // colour head: q / v1 tile written, its MMA done, accumulator drained
 
 struct MlpTc {
     int in_ch, enc_dim, KE;          // 3|4, 63|84, 64|96
@@ -567,6 +568,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         mbar_init(BAR(H_READY + 1), 4);
         mbar_init(BAR(HEAD_READY), 1);
         mbar_init(BAR(DIR_FREE), 1);
+        mbar_init(BAR(Q_READY), 4);
+        mbar_init(BAR(CH_READY), 1);
+        mbar_init(BAR(HEAD_DONE), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) tmem_alloc(sbase + SM_BAR + 8 * NUM_BARS, 512);
@@ -889,6 +893,32 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 TLAP(tm_hwait);
                 tc_fence_after();
             };
+            // Colour head of a tile: q -> relu -> 64x64 -> relu -> 64x3.  It is software-pipelined INTO the first job of the CTA's next
+            // tile (stage 0 after layer 1's MMAs, stage 1 after layer 2's), so the tensor pipe and the producers never idle behind
+            // its three dependent round trips; operands live in the h=1 half of the H tile, accumulators in the head accumulator.
+            uint32_t ph_q = 0, ph_done = 0;
+            bool pend = false;
+            const uint32_t sQ = sH + 16384;
+            auto wait_bar = [&](int b, uint32_t& ph, int tag) {
+                TLAP(tm_issue);
+                mbar_wait(BAR(b), ph, P.err, tag); ph ^= 1;
+                TLAP(tm_hwait);
+                tc_fence_after();
+            };
+            auto color_stage = [&](int stage) {
+                wait_bar(Q_READY, ph_q, 14 + stage);
+                if (elect_one()) {
+                    if (stage == 0) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) mma_ss(dH, desc_sw128(sQ + ks * 32), desc_sw128(sWH + WH_V1 + ks * 32), id_q, ks > 0);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) mma_ss(dH + 64, desc_sw128(sQ + ks * 32), desc_sw128(sWH + WH_RGB + ks * 32), id_rgb, ks > 0);
+                    }
+                    tc_commit(BAR(CH_READY));
+                }
+                __syncwarp();
+            };
             for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
                 for (int v = 0; v < nv; ++v) {
                     for (int h = 0; h < 2; ++h, ++kcount) {
@@ -947,10 +977,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                                 }
                                 __syncwarp();
                             }
+                            if (pend && v == 0 && h == 0 && l < 3) color_stage(l - 1);
                         }
                         wait_h(0, 13);                              // h3 of both blocks written
                         wait_h(1, 13);
                     }
+                    // the previous tile's colour head (drained during this tile's first job) has left the head accumulator
+                    if (v == 0 && pend) { wait_bar(HEAD_DONE, ph_done, 17); pend = false; }
                     // head: Dh (+)= H3 . (Whead_h)^T      (128 points on lanes, accumulates the view mean)
                     if (elect_one()) {
 #pragma unroll
@@ -966,24 +999,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                     }
                     __syncwarp();
                 }
-                // colour head: q -> relu -> 64x64 -> relu -> 64x3   (uses block-0 barriers)
-                wait_h(0, 14);
-                if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_V1 + ks * 32), id_q, ks > 0);
-                    tc_commit(BAR(ACC_READY));
-                }
-                __syncwarp();
-                wait_h(0, 15);
-                if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) mma_ss(dD, desc_sw128(sH + ks * 32), desc_sw128(sWH + WH_RGB + ks * 32), id_rgb, ks > 0);
-                    tc_commit(BAR(ACC_READY));
-                }
-                __syncwarp();
-                // accumulator drained by the colour epilogue before the next tile overwrites it
-                wait_h(0, 16);
+                pend = true;        // colour head of this tile: interleaved with the first job of the next tile (or drained below)
             }
+            if (pend) { color_stage(0); color_stage(1); wait_bar(HEAD_DONE, ph_done, 18); }
             if (DBG && P.dbg && lane == 0) {
                 long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
                 d[6] = tm_encwait; d[7] = tm_hwait; d[8] = tm_issue; d[13] = tm_gwait;
@@ -1001,6 +1019,73 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         TSTART();
         const uint32_t hbase = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u;     // MN-major H: atom of 8 K rows, row c&7
         const uint32_t sH = sbase + SM_H, sBias = sbase + SM_BIAS;
+        // ---- head epilogue of tile (g_, q_): thread = point row c.  Three stages, each behind one colour-head MMA; they are
+        //      interleaved with the trunk epilogues of the next tile's first job (after layers 0, 1, 2), or run back to back for
+        //      the CTA's last tile.  Tiles of the colour head live in the h=1 half of H, accumulators in the head accumulator. ----
+        bool pend = false;
+        int pg = 0, pq = 0;
+        uint32_t ph_ch = 0;
+        const uint32_t sQ = sH + 16384;
+        auto head_stage = [&](int stage, int g_, int q_) {
+            TLAP(te_work);
+            const int rl = c & 31, sl = c >> 5;
+            const int slot_r = g_ * kTileRays + rl, s = q_ * kTileSamples + sl;
+            const bool valid = slot_r < P.n_rays && s < N;
+            const int rid = P.ray_order ? P.ray_order[min(slot_r, P.n_rays - 1)] : min(slot_r, P.n_rays - 1);
+            const long long gp = (long long)rid * N + min(s, N - 1);
+            if (stage == 0) {
+                mbar_wait(BAR(HEAD_READY), ph_head, P.err, 26); ph_head ^= 1;
+                tc_fence_after();
+                uint32_t r[80];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
+                tc_wait_ld();
+                const float raw = __uint_as_float(r[64]) + lds_f32(sBias + 4 * 644);
+                const float xs = raw - 1.0f;                                       // model.py:392-393
+                if (valid) P.sigma_out[gp] = xs > 20.f ? xs : log1pf(expf(xs));
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (512 + ch * 8 + i)), 0.f);
+                    sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
+                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                }
+                tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
+            } else if (stage == 1) {
+                mbar_wait(BAR(CH_READY), ph_ch, P.err, 27); ph_ch ^= 1;
+                tc_fence_after();
+                uint32_t r[64];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
+                tc_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (576 + ch * 8 + i)), 0.f);
+                    sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
+                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                }
+                tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
+            } else {
+                mbar_wait(BAR(CH_READY), ph_ch, P.err, 28); ph_ch ^= 1;
+                tc_fence_after();
+                uint32_t r[16];
+                tmem_ld16(lane_base + TM_DH + 64, r);
+                tc_wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float a = __uint_as_float(r[k]) + lds_f32(sBias + 4 * (640 + k));
+                        P.rgb_out[gp * 3 + k] = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;   // model.py:395-397
+                    }
+                }
+                tc_fence_before(); mbar_arrive_warp(BAR(HEAD_DONE), lane);
+                pend = false;
+            }
+            TLAP(te_head);
+        };
         for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
@@ -1037,70 +1122,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             fence_proxy_async();
                             mbar_arrive_warp(BAR(H_READY + bb), lane);
                         }
+                        if (pend && v == 0 && h == 0 && l < 3) head_stage(l, pg, pq);
                     }
                 }
             }
-            // ---- head epilogue: thread = point row c ----
-            TLAP(te_work);
-            const int rl = c & 31, sl = c >> 5;
-            const int slot_r = g * kTileRays + rl, s = q * kTileSamples + sl;
-            const bool valid = slot_r < P.n_rays && s < N;
-            const int rid = P.ray_order ? P.ray_order[min(slot_r, P.n_rays - 1)] : min(slot_r, P.n_rays - 1);
-            const long long gp = (long long)rid * N + min(s, N - 1);
-            mbar_wait(BAR(HEAD_READY), ph_head, P.err, 26); ph_head ^= 1;
-            tc_fence_after();
-            {
-                uint32_t r[80];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
-                tc_wait_ld();
-                const float raw = __uint_as_float(r[64]) + lds_f32(sBias + 4 * 644);
-                const float xs = raw - 1.0f;                                       // model.py:392-393
-                if (valid) P.sigma_out[gp] = xs > 20.f ? xs : log1pf(expf(xs));
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (512 + ch * 8 + i)), 0.f);
-                    sts128(sH + c * 128 + ((ch ^ (c & 7)) << 4),
-                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
-                }
-            }
-            tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(H_READY), lane);
-            mbar_wait(BAR(ACC_READY), ph_acc & 1u, P.err, 27); ph_acc ^= 1u;
-            tc_fence_after();
-            {
-                uint32_t r[64];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) tmem_ld16(lane_base + TM_D + 16 * j, r + 16 * j);
-                tc_wait_ld();
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (576 + ch * 8 + i)), 0.f);
-                    sts128(sH + c * 128 + ((ch ^ (c & 7)) << 4),
-                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
-                }
-            }
-            tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(H_READY), lane);
-            mbar_wait(BAR(ACC_READY), ph_acc & 1u, P.err, 28); ph_acc ^= 1u;
-            tc_fence_after();
-            {
-                uint32_t r[16];
-                tmem_ld16(lane_base + TM_D, r);
-                tc_wait_ld();
-                if (valid) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float a = __uint_as_float(r[k]) + lds_f32(sBias + 4 * (640 + k));
-                        P.rgb_out[gp * 3 + k] = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;   // model.py:395-397
-                    }
-                }
-            }
-            tc_fence_before(); mbar_arrive_warp(BAR(H_READY), lane);
-            TLAP(te_head);
+            pend = true; pg = g; pq = q;       // colour head of this tile: interleaved with the next tile's first job (or drained below)
         }
+        if (pend) { head_stage(0, pg, pq); head_stage(1, pg, pq); head_stage(2, pg, pq); }
         if (DBG && P.dbg && threadIdx.x == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
             d[9] = te_accwait; d[10] = te_gwait; d[11] = te_work; d[12] = te_head;
