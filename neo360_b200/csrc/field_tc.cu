@@ -751,7 +751,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         const ViewXform vx = vxs[v];
                         float ce[4], cl[3];
                         to_camera(vx, pr.xe, ce);
-                        to_camera(vx, pr.xl, cl);
+                        if (IS_BG) to_camera(vx, pr.xl, cl);
+                        else { cl[0] = ce[0]; cl[1] = ce[1]; cl[2] = ce[2]; }      // foreground: the lookup point IS the encoded point
                         ce[3] = pr.tv;
                         Taps tp;
                         if (sub == 0) {
@@ -764,7 +765,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             bilinear_taps(ga, gb, P.sc.plane_w, P.sc.plane_h, tp);
                         }
                         // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w)
-                        const bool dead = (tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f);   // zeros padding
+                        // zeros padding, or a padding row of the tile (sample index past N / ray past the batch: its outputs are never stored)
+                        const bool dead = ((tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f)) |
+                                          (q * kTileSamples + ((h * kHalfPts + row) >> 5) >= N) | (g * kTileRays + (row & 31) >= P.n_rays);
                         // bit 0 of the first offset: "same texel quad as the previous row" (rows are consecutive lanes; the gather
                         // then keeps the four texels in registers).  Never set on lane 0 or after a dead row.
                         const int pi0 = __shfl_up_sync(0xffffffffu, tp.idx[0], 1), pi1 = __shfl_up_sync(0xffffffffu, tp.idx[1], 1);
