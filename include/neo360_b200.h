@@ -256,11 +256,18 @@ int neo_tc_selftest(const float* X, const float* W, const float* Wn, float* out1
 /* Self-test of the transpose-accumulate MMA that adds gathered features into the trunk accumulators (identity A operand,
  * no-swizzle K-major): outa / outb (128,128) = X^T under the two readings of the descriptor's LBO/SBO fields. */
 int neo_tc_selftest_transpose(const float* X, float* outa, float* outb, void* stream);
+/* Host-side view of the TC kernel's encoding-column layout (csrc/field_tc.cu enc_col<>): for in_ch = 3|4 and operand column
+ * `col` in [0, KE = 64|96) returns the reference's positional-encoding index (helper.py:121-125 order) in [0, 21*in_ch),
+ * -1 for the constant-one (bias) column, -2 for a zero padding column, -3 for invalid arguments.  Pure host code (no GPU). */
+int neo_tc_enc_column(int in_ch, int col);
 
-/* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 16)
- * int64; NULL disables.  Roles and slots are documented in csrc/field_tc.cu. */
+/* Debug: per-CTA cycle accounting of the NEO_PREC_TC field kernel into a caller-zeroed device array of (#SMs x 64)
+ * int64; NULL disables (a separate instantiation of the kernel carries the timers; production launches have none).
+ * Slots: tools/tc_debug.py. */
 int neo_tc_debug(long long* buf);
-/* Debug: sensitivity experiments for profiling -- the TC kernel skips parts of its work (results become wrong); 0 = normal. */
+/* Debug: sensitivity experiments for profiling -- the TC kernel skips parts of its work (results become wrong); 0 = normal.
+ * bit 0: no texel loads / blends, bit 1: zero positional encoding, bit 2: no transpose-accumulate MMAs (gathered features dropped),
+ * bit 3: no texel-quad reuse (every row re-reads its 16 taps; results unchanged). */
 int neo_tc_ablate(int mask);
 
 const char* neo_last_error(void);

@@ -106,6 +106,7 @@ SYMBOLS = {
     "neo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "neo_tc_selftest": (C.c_int, [C.c_void_p] * 8),
     "neo_tc_selftest_transpose": (C.c_int, [C.c_void_p] * 4),
+    "neo_tc_enc_column": (C.c_int, [C.c_int, C.c_int]),
     "neo_tc_debug": (C.c_int, [C.c_void_p]),
     "neo_tc_ablate": (C.c_int, [C.c_int]),
     "neo_last_error": (C.c_char_p, []),

@@ -1417,6 +1417,14 @@ extern "C" int neo_tc_selftest_transpose(const float* X, float* outa, float* out
     NEO_LAUNCH_CHECK("selftest_transpose_kernel");
     return NEO_OK;
 }
+extern "C" int neo_tc_enc_column(int in_ch, int col) {
+    using namespace neo::tc;
+    if ((in_ch != 3 && in_ch != 4) || col < 0 || col >= (in_ch == 3 ? 64 : 96)) return -3;
+    const EncCol e = (in_ch == 3) ? enc_col<3>(col) : enc_col<4>(col);
+    if (e.kind == 1) return -1;
+    if (e.kind == 0) return -2;
+    return (in_ch == 3) ? enc_col_ref_index<3>(col) : enc_col_ref_index<4>(col);
+}
 extern "C" int neo_tc_debug(long long* buf) { neo::g_dbg = buf; return NEO_OK; }
 // Debug: sensitivity experiments -- the kernel skips parts of its work (results become wrong!): see Params::ablate.
 extern "C" int neo_tc_ablate(int mask) { neo::g_ablate = mask; return NEO_OK; }

@@ -44,6 +44,25 @@ def test_argument_validation_without_gpu(lib):
     assert lib.neo_field_eval(None, None, None, None, 8, 0, 0, None, None, None) == -1
 
 
+@pytest.mark.parametrize("in_ch,ke", [(3, 64), (4, 96)])
+def test_tc_encoding_column_layout_is_a_permutation(lib, in_ch, ke):
+    """The TC kernel orders the positional-encoding columns per coordinate (x, sin 2^k x, cos 2^k x) so that the double-angle
+    recurrence applies; the weight image is permuted with the same table.  It must cover every reference column
+    (helper.py:121-125 order) exactly once, carry exactly one constant-one (bias) column and only zero padding otherwise."""
+    cols = [lib.neo_tc_enc_column(in_ch, c) for c in range(ke)]
+    ref = sorted(c for c in cols if c >= 0)
+    assert ref == list(range(21 * in_ch))
+    assert cols.count(-1) == 1 and cols.count(-2) == ke - 21 * in_ch - 1
+    # per-coordinate grouping: column of x_c, then its 10 sines (levels ascending), then its 10 cosines
+    stride = 21 if in_ch == 3 else 24
+    for cc in range(in_ch):
+        base = cc * stride
+        assert cols[base] == cc
+        assert cols[base + 1:base + 11] == [in_ch + k * in_ch + cc for k in range(10)]
+        assert cols[base + 11:base + 21] == [in_ch + 10 * in_ch + k * in_ch + cc for k in range(10)]
+    assert lib.neo_tc_enc_column(5, 0) == -3 and lib.neo_tc_enc_column(3, 64) == -3
+
+
 def test_struct_layout_matches_header():
     """sizeof of the ctypes mirrors == what a C compiler lays out for the header (guards silent ABI drift)."""
     import subprocess, tempfile
