@@ -9,12 +9,17 @@
 //       sigma_raw = (w_sigma / NV) . sum_v h3_v + b_sigma
 //     i.e. the cross-view means become accumulation over the views in one TMEM accumulator.
 //   * trunk layers run transposed, D^T[neuron][point] = W[neuron][k] . X[point][k]:  the weights are the A operand and
-//     live in TMEM for the whole kernel (tcgen05.mma with A from TMEM), the activations X (fp16, K-major, 128B swizzle)
-//     are the B operand in shared memory; the epilogue thread owns a neuron, so its bias is a register.
+//     live in TMEM for the whole kernel (tcgen05.mma with A from TMEM), the activations X (fp16, 128B swizzle) are the
+//     B operand in shared memory.
+//   * everything additive rides on the tensor pipe: biases through a K=16 "bias MMA" (b1, b2) or a constant-one encoding
+//     column (b0, b3); the gathered features G[point][channel] through a transpose-accumulate MMA whose A operand is a
+//     shifted-identity tile; the layer-3 skip input is accumulated into a second accumulator at layer-0 time.  The
+//     epilogue is tcgen05.ld -> cvt.f16x2 -> max.f16x2 -> 16-byte shared stores.
 //
 // One CTA per SM, persistent over tiles of 128 points (32 rays x 4 consecutive samples); per tile the NV source views
-// are processed in turn.  Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issue, 5-15 producers (geometry,
-// positional encoding, tap tables, tap gathers).  Hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+// are processed in turn, each as two half-jobs of 64 points.  Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issue,
+// 5-15 producers (geometry, positional encoding, tap tables, tap gathers with texel-quad reuse).  Hand-offs are
+// mbarriers; tcgen05.commit signals MMA completion and releases producer slots.  DESIGN.md section 5 has the full story.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -34,7 +39,7 @@ constexpr uint32_t SM_H = 32768;          // 128 x 128 fp16, 2 slabs
 constexpr uint32_t SM_DIR = 65536;        // 128 x 64 fp16 (32 used), 1 slab
 constexpr uint32_t SM_WHEAD = 81920;      // head weights, B operands
 constexpr uint32_t WH_H = 0, WH_DIR = 20480, WH_V1 = 30720, WH_RGB = 38912, WH_BYTES = 40960;
-constexpr uint32_t SM_G0 = 122880;        // 2 slots x (64 x 128 fp16 row-major)
+constexpr uint32_t SM_G0 = 122880;        // 2 slots x (64 points x 128 channels fp16, SW128 K-major, 2 slabs): B operand of the transpose-accumulate MMA
 constexpr uint32_t SM_G3 = 155648;
 constexpr uint32_t SM_ROWTAB = 188416;    // 2 slots x (64 rows x 128 B)
 constexpr uint32_t SM_BIAS = 204800;      // fp32: b0..b3 (512) | bq (64) | bv1 (64) | brgb (4) | bsig (1)
@@ -48,9 +53,9 @@ constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB =
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t TM_D = 0;        // trunk accumulator of layers 0-2 (2 blocks x 32 points) ; also Dq (64) / Drgb (16)
-constexpr uint32_t TM_D3 = 64;      // layer-3 accumulator (2 x 32): seeded with W3enc.ENC at layer-0 time so the ENC / G slots free early
-constexpr uint32_t TM_DH = 128;     // head accumulator (80)
+constexpr uint32_t TM_D = 0;        // trunk accumulator of layers 0-2 (2 blocks x 32 points)
+constexpr uint32_t TM_D3 = 64;      // layer-3 accumulator (2 x 32): seeded with W3enc.ENC + b3 + G3 at layer-0 time so the ENC / G slots free early
+constexpr uint32_t TM_DH = 128;     // head accumulator (80: 64 q + sigma + pad); afterwards the colour head's accumulators (64 | 16)
 constexpr uint32_t TM_BIAS = 208;   // A tile (K = 16) of the bias MMA: k = l holds the bias of trunk layer l (fp16)
 constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   (fp16 pairs per column)
 
@@ -84,10 +89,10 @@ struct Params {
     float* sigma_out;
     int* err;
     long long* dbg;     // optional [gridDim.x][kDbgStride] cycle counters (neo_tc_debug), null in production
-    int ablate;         // debug only (neo_tc_ablate): 1 no tap loads, 2 no pos-enc math, 4 no G reads in the epilogue, 8 no MMAs
+    int ablate;         // debug only (neo_tc_ablate): 1 no tap loads/blends, 2 zero pos-enc, 4 no transpose-accumulate MMAs, 8 no quad reuse
 };
 
-// cycle accounting for neo_tc_debug (one representative thread per role); compiled in, costs two CS2R when enabled
+// back-off of the producers' slot waits (they run ahead of the tensor pipeline; see mbar_wait)
 #ifndef NEO_PROD_SLEEP_NS
 #define NEO_PROD_SLEEP_NS 100
 #endif
