@@ -83,3 +83,22 @@ def test_renderer_refuses_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA"):
         net.set_scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"], sc["src_focal"],
                       sc["src_c"], sc["img_wh"])
+
+
+@pytest.mark.parametrize("wh", [(640, 480), (48, 36), (37, 23)])
+def test_blocked_frame_order_is_a_block_permutation(wh):
+    """Host logic of the 8x4-pixel-block ray schedule (renderer._blocked_order): a permutation of the frame's pixels; when the frame
+    is a multiple of 8x4, every run of 32 consecutive slots is exactly one 8x4 pixel block in row-major order inside the block."""
+    import torch
+    from neo360_b200 import NeRF_TP
+    W, H = wh
+    net = NeRF_TP(num_coarse_samples=8, num_fine_samples=4, precision="tc").eval()
+    order = net._blocked_order(W * H, (W, H), torch.device("cpu")).long()
+    assert order.dtype == torch.int64 and order.numel() == W * H
+    assert torch.equal(torch.sort(order).values, torch.arange(W * H))
+    if W % 8 == 0 and H % 4 == 0:
+        blk = order.view(-1, 32)
+        y, x = blk // W, blk % W
+        assert torch.equal(y - y[:, :1], torch.arange(32).div(8, rounding_mode="floor").expand_as(y))
+        assert torch.equal(x - x[:, :1], (torch.arange(32) % 8).expand_as(x))
+        assert bool((x[:, 0] % 8 == 0).all()) and bool((y[:, 0] % 4 == 0).all())
