@@ -769,7 +769,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             const float gb = (sub == 2) ? cl[1] : cl[2];          // xz, xy, yz
                             bilinear_taps(ga, gb, P.sc.plane_w, P.sc.plane_h, tp);
                         }
-                        // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w)
+                        // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w); the eight
+                        // 16-byte chunks of a row are XOR-swizzled by the row (lanes = rows at a 128-byte stride would otherwise all hit
+                        // the same four banks: a 32-way conflict on both stores)
                         // zeros padding, or a padding row of the tile (sample index past N / ray past the batch: its outputs are never stored)
                         const bool dead = ((tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f)) |
                                           (q * kTileSamples + ((h * kHalfPts + row) >> 5) >= N) | (g * kTileRays + (row & 31) >= P.n_rays);
@@ -779,9 +781,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         const int pi2 = __shfl_up_sync(0xffffffffu, tp.idx[2], 1), pi3 = __shfl_up_sync(0xffffffffu, tp.idx[3], 1);
                         const bool pdead = __shfl_up_sync(0xffffffffu, (int)dead, 1) != 0;
                         const bool same = (lane > 0) & !pdead & (pi0 == tp.idx[0]) & (pi1 == tp.idx[1]) & (pi2 == tp.idx[2]) & (pi3 == tp.idx[3]);
-                        sts128(rowtab + row * 128 + sub * 32, make_uint4(dead ? 0xFFFFFFFFu : ((uint32_t)(tp.idx[0] * 32) | (same ? 1u : 0u)),
+                        sts128(rowtab + row * 128 + (((sub * 2) ^ (row & 7)) << 4), make_uint4(dead ? 0xFFFFFFFFu : ((uint32_t)(tp.idx[0] * 32) | (same ? 1u : 0u)),
                                                                           tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
-                        sts128(rowtab + row * 128 + sub * 32 + 16, make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
+                        sts128(rowtab + row * 128 + (((sub * 2 + 1) ^ (row & 7)) << 4), make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
                                                                                pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
                         {
                             const bool zero = (P.ablate & 2) != 0;
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             // the second hidden behind the texel loads) instead of eight dependent ones
                             uint4 off[4];
 #pragma unroll
-                            for (int m = 0; m < 4; ++m) off[m] = lds128(rowtab + r * 128 + m * 32);
+                            for (int m = 0; m < 4; ++m) off[m] = lds128(rowtab + r * 128 + (((m * 2) ^ (r & 7)) << 4));
                             bool live[4];
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
@@ -842,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             }
                             uint4 wq[4];
 #pragma unroll
-                            for (int m = 0; m < 4; ++m) wq[m] = lds128(rowtab + r * 128 + m * 32 + 16);
+                            for (int m = 0; m < 4; ++m) wq[m] = lds128(rowtab + r * 128 + (((m * 2 + 1) ^ (r & 7)) << 4));
                             __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
