@@ -29,8 +29,11 @@ N_COARSE, N_FINE, NV, CHUNK = 128, 64, 3, 1024
 FLOP_PER_POINT = {0: 2 * 770688, 1: 2 * 786816}          # fg, bg
 POINTS_PER_RAY = (N_COARSE + 1) + (N_COARSE + 1 + N_FINE)  # per branch
 FLOP_PER_RAY = POINTS_PER_RAY * (FLOP_PER_POINT[0] + FLOP_PER_POINT[1])   # 1.003 GFLOP
-# MACs the TC path actually issues per point: per view trunk 128*(KE+128+128+128+KE) + head 80*128, plus once 80*32 + 64*64 + 16*64
-ISSUED_MAC_PER_POINT = 0.5 * sum(3 * (128 * (2 * ke + 384) + 80 * 128) + 80 * 32 + 64 * 64 + 16 * 64 for ke in (64, 96))
+# MACs the TC path actually needs per point (mean of fg/bg): per view the re-associated trunk 128*(KE+128+128+128+KE), the bilinear
+# blend of the 4 maps (16 taps x 256 projected channels, on the tensor pipe since round 2) and the folded head 80*128; once per
+# point the direction / colour head 80*32 + 64*64 + 16*64.  Padding of the tcgen05 tiles (window slots without a tap, K 63->64) is
+# NOT counted: this is the useful work the tensor pipe has to do, the denominator of the honest roofline fraction.
+ISSUED_MAC_PER_POINT = 0.5 * sum(3 * (128 * (2 * ke + 384) + 16 * 256 + 80 * 128) + 80 * 32 + 64 * 64 + 16 * 64 for ke in (64, 96))
 
 
 def parse():
@@ -42,7 +45,8 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("NEO360_PRECISION", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--rays", type=int, default=IMG_W * IMG_H, help="debug only: fewer rays per step (not a valid headline)")
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="debug: skip the CPU oracle leg (and with it the parity block)")
+    ap.add_argument("--no-extras", action="store_true", help="debug: skip the eager-GPU reference leg and the call-pattern variants")
     return ap.parse_args()
 
 
@@ -141,11 +145,52 @@ def cpu_reference_rate(sc, P, n_rays, steps=1, warmup=0, threads=None):
     with torch.no_grad():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            orc.render_chunked(rays, osc, P, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+            out = orc.render_chunked(rays, osc, P, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
+    cpu_reference_rate.last = (rays, out)          # the oracle's pixels of the sample: bench's parity block compares against them
     return n_rays * len(times) / sum(times), times, threads
+
+
+def eager_gpu_rates(sc, P, dev, steps=2, warmup=1, n_chunks=8):
+    """The reference ALGORITHM (oracle port = the same eager torch ops the reference issues, F.grid_sample lookups, encoder
+    hoisted) on this GPU: the stand-in for "the reference's PyTorch-GPU path" that the >=10x target names (/root/reference
+    itself cannot travel to the GPU box).  fp32 with TF32 matmuls off and on (the authors' torch 1.11 defaulted to TF32)."""
+    import torch
+    from oracle import neo360_oracle as orc
+    osc = orc.Scene(*[sc[k].to(dev) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses")],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
+    Pd = {k: v.to(dev) for k, v in P.items()}
+    o, d = frame_rays_cpu(0)
+    n = n_chunks * CHUNK
+    start = (IMG_H // 2) * IMG_W
+    rays = {"rays_o": o[start:start + n].to(dev), "rays_d": d[start:start + n].to(dev), "viewdirs": d[start:start + n].to(dev)}
+    res, outs = {"rays": n}, {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            for _ in range(warmup):
+                orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
+            e1.record()
+            torch.cuda.synchronize()
+        res["tf32" if tf32 else "fp32"] = n * steps / (e0.elapsed_time(e1) * 1e-3)
+        outs[tf32] = out
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    # the reference's own TF32-vs-fp32 deviation on these rays: the noise floor SURVEY.md 8(d) asks for
+    res["tf32_vs_fp32_linf_rgb"] = float((outs[True]["comp_rgb"] - outs[False]["comp_rgb"]).abs().max())
+    res["tf32_vs_fp32_psnr"] = orc.psnr(outs[True]["comp_rgb"].cpu(), outs[False]["comp_rgb"].cpu())
+    res["note"] = "oracle port (reference algorithm, eager torch ops incl. F.grid_sample) on the same GPU, encoder hoisted, chunk=1024"
+    del osc, Pd
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -173,41 +218,15 @@ def main():
         return
 
     if args.impl == "eager-gpu":
-        # Informational: the reference ALGORITHM (oracle port = the same eager torch ops the reference issues, encoder
-        # hoisted) run on the GPU -- the stand-in for "the reference's PyTorch-GPU path" that the >=10x target names
-        # (/root/reference itself cannot travel to the GPU box).  fp32 with TF32 matmuls off and on.
         if rank != 0:
             return
         import torch
-        from oracle import neo360_oracle as orc
-        dev = torch.device("cuda", local)
         sc, P = build_scene_cpu()
-        osc = orc.Scene(*[sc[k].to(dev) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses")],
-                        float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), IMG_W, IMG_H)
-        Pd = {k: v.to(dev) for k, v in P.items()}
-        o, d = frame_rays_cpu(0)
-        n = 8 * CHUNK
-        start = (IMG_H // 2) * IMG_W
-        rays = {"rays_o": o[start:start + n].to(dev), "rays_d": d[start:start + n].to(dev), "viewdirs": d[start:start + n].to(dev)}
-        res = {}
-        for tf32 in (False, True):
-            torch.backends.cuda.matmul.allow_tf32 = tf32
-            torch.backends.cudnn.allow_tf32 = tf32
-            with torch.no_grad():
-                for _ in range(args.warmup):
-                    orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(args.steps):
-                    orc.render_chunked(rays, osc, Pd, N_COARSE, N_FINE, chunk=CHUNK, lookup_impl="aten")
-                e1.record()
-                torch.cuda.synchronize()
-            res["tf32" if tf32 else "fp32"] = n * args.steps / (e0.elapsed_time(e1) * 1e-3)
+        res = eager_gpu_rates(sc, P, torch.device("cuda", local), steps=args.steps, warmup=args.warmup)
         print(json.dumps({"impl": "eager-gpu", "metric": "rays/sec at 640x480, 192 samples/ray", "unit": "rays/s",
                           "value": res["fp32"], "value_tf32": res["tf32"], "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-                          "config": {"workload": workload, "rays_per_step": n, "chunk": CHUNK,
-                                     "note": "oracle port (reference algorithm, eager torch ops incl. F.grid_sample) on the GPU, encoder hoisted"}}))
+                          "config": {"workload": workload, "rays_per_step": res["rays"], "chunk": CHUNK, "note": res["note"]},
+                          "tf32_vs_fp32": {"linf_rgb": res["tf32_vs_fp32_linf_rgb"], "psnr": res["tf32_vs_fp32_psnr"]}}))
         return
 
     import torch
@@ -288,6 +307,38 @@ def main():
     lib.neo_profile_read(None, None, C.byref(launches), None)
     net.check()
     ms_e2e = timed(step_e2e)
+    variants = {}
+    if world == 1 and not args.no_extras and n == IMG_W * IMG_H:
+        from neo360_b200 import ops
+        pose_host = [__import__("neo360_b200").synth.target_pose(v, 100)[:3, :4].contiguous().pin_memory() for v in range(4)]
+
+        def step_pose(s):
+            # rays generated on the device from the (3,4) pose (datasets/ray_utils.py:84-176) -- 48 bytes of H2D per frame
+            c2w = pose_host[s % len(pose_host)].to(dev, non_blocking=True)
+            ro, vd, rd, _ = ops.get_rays(IMG_H, IMG_W, 0.8 * IMG_W, c2w)
+            r = net.render_rays_test({"rays_o": ro, "rays_d": rd, "viewdirs": vd}, chunk=CHUNK, img_wh=wh)
+            out_host[:, :3].copy_(r["rgb"], non_blocking=True)
+            out_host[:, 3].copy_(r["depth"], non_blocking=True)
+
+        def step_chunked(s):
+            # the UNCHANGED reference render loop (models/neo360/model.py:861-896): one model(...) call per 1024-ray chunk
+            o, d = host[s % len(host)]
+            do, dd = o.to(dev, non_blocking=True), d.to(dev, non_blocking=True)
+            outs = []
+            for i in range(0, n, CHUNK):
+                outs.append(net({"rays_o": do[i:i + CHUNK], "rays_d": dd[i:i + CHUNK], "viewdirs": dd[i:i + CHUNK]},
+                                False, False, None, None, out_depth=True)[1])
+            rgb = torch.cat([x[0] for x in outs]); dep = torch.cat([x[5] for x in outs])
+            out_host[:, :3].copy_(rgb, non_blocking=True)
+            out_host[:, 3].copy_(dep, non_blocking=True)
+
+        keep_steps, keep_warm = args.steps, args.warmup
+        args.steps, args.warmup = 2, 1
+        variants["pose_in_rays_on_device"] = {"value": n * args.steps / (timed(step_pose) * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48,
+                                              "note": "e2e with neo_get_rays on the device from an H2D (3,4) pose instead of host-built rays"}
+        variants["per_chunk_calls"] = {"value": n * args.steps / (timed(step_chunked) * 1e-3), "unit": "rays/s", "calls_per_frame": (n + CHUNK - 1) // CHUNK,
+                                       "note": "e2e through the reference's unchanged chunk loop: one NeRF_TP.forward per 1024 rays"}
+        args.steps, args.warmup = keep_steps, keep_warm
     # roofline of the dominant kernel: CUDA events around every field launch, on the launching stream
     lib.neo_profile(1)
     with torch.no_grad():
@@ -307,7 +358,11 @@ def main():
     e2e = rays_total / (ms_e2e * 1e-3)
     # each field launch handles one branch; fg and bg launches alternate, so the mean flop/point is the fg/bg average
     flops_alg = pts.value * 0.5 * (FLOP_PER_POINT[0] + FLOP_PER_POINT[1])
-    ach = flops_alg / (fms.value * 1e-3) / 1e12
+    flops_issued = pts.value * 2.0 * ISSUED_MAC_PER_POINT if args.precision == "tc" else flops_alg
+    ach = flops_issued / (fms.value * 1e-3) / 1e12                       # what the tensor pipe really does per second
+    ach_ref = flops_alg / (fms.value * 1e-3) / 1e12                      # reference-formulation FLOPs per second of field-kernel time
+    # reference-formulation figure with the per-scene pre-projection charged to ONE frame (SURVEY.md 8(d)'s condition for quoting it)
+    ach_ref_charged = flops_alg / ((fms.value + args.steps * scene_prepare_ms) * 1e-3) / 1e12
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -325,21 +380,44 @@ def main():
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": ach / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["src"],
                      "kernel": "field kernel (lookups + MLP), %d launches, %.3f ms mean" % (nf.value, fms.value / max(nf.value, 1)),
-                     "flops": "reference-formulation algorithmic FLOPs (2*MAC of NeRFPPMLP incl. latent columns), SURVEY.md 8(d)",
+                     "flops": "FLOPs the tensor pipe has to issue for the re-associated network (2*MAC: trunk on pre-projected maps, bilinear "
+                              "blend, folded head; tile padding not counted) / CUDA-event time of the field launches",
                      "share_of_step": (fms.value / args.steps) / (ms_res / args.steps),
-                     "issued_tflops": (pts.value * 2.0 * ISSUED_MAC_PER_POINT) / (fms.value * 1e-3) / 1e12 if args.precision == "tc" else ach,
-                     "note": "TC path issues fewer FLOPs than the reference formulation (latent columns pre-applied to the feature maps once per scene, "
-                             "bottleneck folded into the view layer); scene_prepare_ms is that per-scene cost, amortised over every frame of the scene"},
+                     "effective_tflops": ach_ref, "effective_frac": ach_ref_charged / pk["bf16_tflops"],
+                     "note": "effective_* = reference-formulation algorithmic FLOPs (2*MAC of NeRFPPMLP incl. the latent columns, SURVEY.md 8(d)); "
+                             "effective_frac charges scene_prepare_ms (the per-scene pre-projection that removes those FLOPs) to every frame"},
         "scene_prepare_ms": scene_prepare_ms,
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 2 * n * 3 * 4, "d2h_bytes_per_step": n * 4 * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches.value),
         "clocks": sampler.result(),
     }
+    if not args.no_extras and world == 1:
+        line["variants"] = variants
     if not args.no_cpu_baseline and world == 1:
         rate, times, threads = cpu_reference_rate(sc, P, args.cpu_sample_rays, steps=1, warmup=0)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_sample_rays} rays (one reference chunk of frame 0), {times[0]:.1f} s"}
+        # PSNR / L-inf of OUR pixels against the oracle's on exactly that sample (BASELINE.json: "... ; PSNR vs ref"):
+        # the chunk is rendered the way the reference would (a standalone chunk of `chunk` rays, quirk Q1)
+        from oracle import neo360_oracle as orc
+        rays_cpu, ref = cpu_reference_rate.last
+        with torch.no_grad():
+            got = net.render_rays_test({k: v.to(dev) for k, v in rays_cpu.items()}, chunk=CHUNK)
+        net.check()
+        line["parity"] = {"rays": int(args.cpu_sample_rays), "vs": "oracle port (fp32, CPU) on the cpu_baseline sample",
+                          "linf_rgb": float((got["rgb"].cpu() - ref["comp_rgb"]).abs().max()),
+                          "linf_depth": float((got["depth"].cpu() - ref["depth"]).abs().max()),
+                          "linf_acc": float((got["fg_acc"].cpu() - ref["fg_acc"]).abs().max()),
+                          "psnr_vs_ref": orc.psnr(got["rgb"].cpu(), ref["comp_rgb"])}
+    if not args.no_extras and world == 1:
+        # the reference's eager-PyTorch formulation on this GPU: denominator of the >=10x target
+        del net
+        torch.cuda.empty_cache()
+        eg = eager_gpu_rates(sc, P, dev)
+        eg["speedup_vs_fp32"] = e2e / eg["fp32"]
+        eg["speedup_vs_tf32"] = e2e / eg["tf32"]
+        line["eager_gpu"] = eg
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -108,7 +108,8 @@ SYMBOLS = {
     "neo_tc_selftest_transpose": (C.c_int, [C.c_void_p] * 4),
     "neo_tc_enc_column": (C.c_int, [C.c_int, C.c_int]),
     "neo_tc_debug": (C.c_int, [C.c_void_p]),
-    "neo_tc_ablate": (C.c_int, [C.c_int]),
+    "neo_tc_selftest_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "neo_tc_trap_info": (C.c_char_p, []),
     "neo_last_error": (C.c_char_p, []),
     "neo_version": (C.c_char_p, []),
 }
@@ -136,7 +137,7 @@ def load():
 
 def check(rc: int):
     if rc != 0:
-        raise RuntimeError(f"neo360_b200 error {rc}: {load().neo_last_error().decode()}")
+        raise RuntimeError(f"neo360_b200 error {rc}: {load().neo_last_error().decode()}{load().neo_tc_trap_info().decode()}")
 
 
 def ptr(t):

@@ -12,16 +12,25 @@
 //     live in TMEM for the whole kernel (tcgen05.mma with A from TMEM), the activations X (fp16, 128B swizzle) are the
 //     B operand in shared memory.
 //   * everything additive rides on the tensor pipe: biases through a K=16 "bias MMA" (b1, b2) or a constant-one encoding
-//     column (b0, b3); the gathered features G[point][channel] through a transpose-accumulate MMA whose A operand is a
-//     shifted-identity tile; the layer-3 skip input is accumulated into a second accumulator at layer-0 time.  The
+//     column (b0, b3); the layer-3 skip input is accumulated into a second accumulator at layer-0 time.  The
 //     epilogue is tcgen05.ld -> cvt.f16x2 -> max.f16x2 -> 16-byte shared stores.
+//   * the bilinear lookups themselves run on the tensor pipe: the projected maps are stored as 64-channel groups
+//     [view*4 + group][y][x][64] so that ONE TMA box load (cp.async.bulk.tensor.4d, 128B swizzle) stages a 4x4 texel
+//     window of all 256 channels as an MN-major A operand; the producers only compute the 2x2 tap weights of each point
+//     and scatter them into a sparse [64 points x 16 texels] B tile.  D[channel][point] += WINDOW^T . TAPW^T is then
+//     the exact zero-padded bilinear blend, accumulated in fp32 (no per-lane gathers, no fp16 blend arithmetic).
+//     A 64-point job touches ~4 windows (quads of neighbouring pixels/samples share texels); windows live in an
+//     8-deep shared-memory ring filled by TMA and released by tcgen05.commit.
 //
 // One CTA per SM, persistent over tiles of 128 points (32 rays x 4 consecutive samples); per tile the NV source views
 // are processed in turn, each as two half-jobs of 64 points.  Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issue,
-// 5-15 producers (geometry, positional encoding, tap tables, tap gathers with texel-quad reuse).  Hand-offs are
+// 5-15 producers (geometry, positional encoding, tap weights, window enumeration + TMA issue).  Hand-offs are
 // mbarriers; tcgen05.commit signals MMA completion and releases producer slots.  DESIGN.md section 5 has the full story.
 #include "common.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdio>
+#include <cstring>
 
 namespace neo {
 namespace tc {
@@ -39,18 +48,22 @@ constexpr uint32_t SM_H = 32768;          // 128 x 128 fp16, 2 slabs
 constexpr uint32_t SM_DIR = 65536;        // 128 x 64 fp16 (32 used), 1 slab
 constexpr uint32_t SM_WHEAD = 81920;      // head weights, B operands
 constexpr uint32_t WH_H = 0, WH_DIR = 20480, WH_V1 = 30720, WH_RGB = 38912, WH_BYTES = 40960;
-constexpr uint32_t SM_G0 = 122880;        // 2 slots x (64 points x 128 channels fp16, SW128 K-major, 2 slabs): B operand of the transpose-accumulate MMA
-constexpr uint32_t SM_G3 = 155648;
-constexpr uint32_t SM_ROWTAB = 188416;    // 2 slots x (64 rows x 128 B)
-constexpr uint32_t SM_BIAS = 204800;      // fp32: b0..b3 (512) | bq (64) | bv1 (64) | brgb (4) | bsig (1)
+constexpr int kRing = 8;                  // texel-window ring depth
+constexpr uint32_t WIN_BYTES = 8192;      // one window: 4 channel groups x (16 texels x 128 B), SW128 MN-major A operand (TMA box 64 x 4 x 4 x 4)
+constexpr uint32_t WT_BYTES = 2048;       // its tap-weight tile: 64 points x 16 texels fp16, no-swizzle K-major B operand
+constexpr uint32_t SM_WIN = 122880;       // kRing x WIN_BYTES
+constexpr uint32_t SM_WT = SM_WIN + kRing * WIN_BYTES;       // 188416: kRing x WT_BYTES
+constexpr uint32_t SM_BIAS = SM_WT + kRing * WT_BYTES;       // 204800: fp32: b0..b3 (512) | bq (64) | bv1 (64) | brgb (4) | bsig (1)
 constexpr uint32_t SM_PTS = 207872;       // per-tile cache: 128 rows x 48 B (world points are view independent)
 constexpr uint32_t SM_VIEWS = 214016;     // kMaxViews x 64 B source-camera transforms
-constexpr uint32_t SM_BAR = 214528;
+constexpr uint32_t SM_BAR = 214528;       // mbarriers (8 B each) + TMEM base slot
 constexpr uint32_t SM_SEL = 215040;       // 32 x 128 B one-hot selector tile (SW128): B operand of the bias MMA, k-step l selects layer l
-constexpr uint32_t SM_IDENT = 219136;     // shifted-identity tile (7680 B, no swizzle): A operand of the transpose-accumulate MMA
-constexpr uint32_t SM_TOTAL = 226816;
-constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_G = 16384, SLOT_TAB = 8192;
+constexpr uint32_t SM_ROWINFO = 219136;   // 2 slots x 4 maps x 64 rows x 16 B: (x0, y0 | dead, w_nw w_ne, w_sw w_se)
+constexpr uint32_t SM_CNT = 227328;       // 2 slots x 4 window counts | ring tail
+constexpr uint32_t SM_TOTAL = 227392;
+constexpr uint32_t SLOT_ENC = 16384, SLAB_ENC = 8192, SLOT_INFO = 4096;
 constexpr int BIAS_FLOATS = 512 + 64 + 64 + 4 + 4;
+constexpr uint32_t kDeadRow = 0x7fffffffu;
 
 // TMEM column map (512 columns allocated)
 constexpr uint32_t TM_D = 0;        // trunk accumulator of layers 0-2 (2 blocks x 32 points)
@@ -62,16 +75,17 @@ constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   
 // slot-indexed barriers come in pairs (slot 0, slot 1)
 // ACC_READY / H_READY are indexed by the 32-point block (0/1) of the half-job: the two blocks ping-pong between the
 // tensor core and the epilogue warps, so MMA latency hides behind the other block's epilogue.
-enum Bar { ENC_READY = 0, ENC_FREE = 2, G_READY = 4, G_FREE = 6, ACC_READY = 8, H_READY = 10, HEAD_READY = 12, DIR_FREE,
-           Q_READY, CH_READY, HEAD_DONE, NUM_BARS };      // colour head: q / v1 tile written, its MMA done, accumulator drained
+enum Bar { ENC_READY = 0, ENC_FREE = 2, CNT_READY = 4, ACC_READY = 6, H_READY = 8, HEAD_READY = 10, DIR_FREE,
+           Q_READY, CH_READY, HEAD_DONE,                  // colour head: q / v1 tile written, its MMA done, accumulator drained
+           WIN_FULL, WIN_EMPTY = WIN_FULL + kRing, NUM_BARS = WIN_EMPTY + kRing };
 
 struct MlpTc {
     int in_ch, enc_dim, KE;          // 3|4, 63|84, 64|96
     const uint32_t* wimg;            // [KW/2][128] TMEM image words
     const float* bias;               // BIAS_FLOATS
     const uint4* headimg;            // WH_BYTES pre-swizzled
-    const __half* plocal;            // [nv][lat_hw][256]
-    const __half* pplane[3];         // [nv][plane_hw][256]
+    const __half* pmap[4];           // projected maps [P0|P3]: latent, xz, xy, yz; layout [nv*4 + channel group][H][W][64]
+    alignas(64) CUtensorMap tmap[4]; // their 4-D TMA descriptors (64 ch, W, H, nv*4), box 64 x 4 x 4 x 4, 128B swizzle
 };
 
 struct State {
@@ -88,8 +102,8 @@ struct Params {
     float* rgb_out;
     float* sigma_out;
     int* err;
+    int* trap;          // host-mapped int[8]: who timed out on which mbarrier (mbar_timeout)
     long long* dbg;     // optional [gridDim.x][kDbgStride] cycle counters (neo_tc_debug), null in production
-    int ablate;         // debug only (neo_tc_ablate): 1 no tap loads/blends, 2 zero pos-enc, 4 no transpose-accumulate MMAs, 8 no quad reuse
 };
 
 // back-off of the producers' slot waits (they run ahead of the tensor pipeline; see mbar_wait)
@@ -97,8 +111,21 @@ struct Params {
 #define NEO_PROD_SLEEP_NS 100
 #endif
 constexpr int kProdSleep = NEO_PROD_SLEEP_NS;
+// consumer-side waits (MMA issue, epilogue): poll NEO_SPIN_POLLS times at full rate (the latency-critical hand-offs complete within
+// that), then back off so that a long wait does not flood the shared-memory / mbarrier pipe the producers' loads and stores need
+#ifndef NEO_SPIN_POLLS
+#define NEO_SPIN_POLLS 16
+#endif
+#ifndef NEO_SPIN_SLEEP_NS
+#define NEO_SPIN_SLEEP_NS 64
+#endif
 constexpr int kDbgStride = 64;
 // cycle accounting (neo_tc_debug): compiled only into the DBG instantiation of the kernel
+// event trace (DBG instantiation, CTA 0, first kTraceJobs half-jobs): int64 stamps at dbg[gridDim.x * kDbgStride + role * 1024 + job * 8 + k]
+constexpr int kTraceJobs = 120;
+#define TRACE(role, job, k, dep) do { if (DBG && P.dbg && blockIdx.x == 0 && (job) < kTraceJobs) { long long _ts; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(_ts) : "r"((uint32_t)(dep)) : "memory"); \
+    P.dbg[(size_t)gridDim.x * kDbgStride + (role) * 1024 + (job) * 8 + (k)] = _ts; } } while (0)
 #define TSTART() long long _t0 = DBG ? clock64() : 0
 #define TLAP(acc) do { if (DBG) { long long _t1 = clock64(); acc += _t1 - _t0; _t0 = _t1; } } while (0)
 
@@ -128,39 +155,57 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Wait on an mbarrier phase: asm loop with an in-register spin bound, so a protocol bug traps (launch failure reported by
-// neo_check_async / the next CUDA call) instead of hanging the GPU.  SLEEP_NS > 0 backs off between polls: used by the producer
-// warps, which run ahead of the tensor pipeline and must not steal issue slots from the epilogue warps sharing their schedulers.
+// neo_check_async / the next CUDA call) instead of hanging the GPU.  Before trapping, the waiter records (tag, CTA, thread, barrier,
+// parity) in a host-mapped buffer, which survives the dead context: neo_tc_trap_info() / neo_check_async print it.
+// SLEEP_NS > 0 backs off between polls: used by the producer warps, which run ahead of the tensor pipeline and must not steal
+// issue slots from the epilogue warps sharing their schedulers.
+__device__ __noinline__ void mbar_timeout(int* trapinfo, int tag, uint32_t bar, uint32_t parity) {
+    if (trapinfo) {
+        volatile int* t = trapinfo;
+        if (t[0] == 0) {
+            t[1] = (int)blockIdx.x; t[2] = (int)threadIdx.x; t[3] = (int)bar; t[4] = (int)parity; t[5] = (int)gridDim.x;
+            t[0] = tag + 1000;
+        }
+        __threadfence_system();
+    }
+    asm volatile("trap;");
+}
 template <int SLEEP_NS = 0>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
-    (void)err; (void)tag;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* trapinfo, int tag) {
+    uint32_t ok;
     if (SLEEP_NS > 0) {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
             "mov.u32 c, 0;\n\t"
+            "mov.u32 %0, 1;\n\t"
             "NEO_WAIT_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "@p bra NEO_DONE_%=;\n\t"
-            "nanosleep.u32 %3;\n\t"
+            "nanosleep.u32 %4;\n\t"
             "add.u32 c, c, 1;\n\t"
-            "setp.lt.u32 q, c, 0x4000000;\n\t"
+            "setp.lt.u32 q, c, 0x800000;\n\t"
             "@q bra NEO_WAIT_%=;\n\t"
-            "trap;\n\t"
+            "mov.u32 %0, 0;\n\t"
             "NEO_DONE_%=:\n\t}"
-            ::"r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)SLEEP_NS) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)SLEEP_NS) : "memory");
     } else {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
             "mov.u32 c, 0;\n\t"
+            "mov.u32 %0, 1;\n\t"
             "NEO_WAIT_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "@p bra NEO_DONE_%=;\n\t"
             "add.u32 c, c, 1;\n\t"
-            "setp.lt.u32 q, c, 0x8000000;\n\t"
+            "setp.gt.u32 q, c, %4;\n\t"
+            "@q nanosleep.u32 %5;\n\t"
+            "setp.lt.u32 q, c, 0x4000000;\n\t"
             "@q bra NEO_WAIT_%=;\n\t"
-            "trap;\n\t"
+            "mov.u32 %0, 0;\n\t"
             "NEO_DONE_%=:\n\t}"
-            ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)NEO_SPIN_POLLS), "r"((uint32_t)NEO_SPIN_SLEEP_NS) : "memory");
     }
+    if (!ok) mbar_timeout(trapinfo, tag, bar, parity);
 }
 // one lane of a fully converged warp (the MMA warp keeps warp-uniform control flow so descriptors stay in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -182,6 +227,17 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: one 4-D box (64 channels x 4 x 4 texels x 4 channel groups) of a projected map -> shared memory (128B swizzle);
+// out-of-range texels are zero-filled, which is exactly grid_sample's zeros padding
+__device__ __forceinline__ void tma_load_window(uint32_t dst, const CUtensorMap* tmap, int x, int y, int g, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(x), "r"(y), "r"(g), "r"(bar) : "memory");
 }
 
 // K-major, 128-byte-swizzled operand descriptor: rows of 128 B (64 fp16), 8-row groups 1024 B apart.
@@ -328,7 +384,9 @@ __host__ __device__ inline uint32_t sw128_off(int row, int k, int rows) {
 // ------------------------------------------------------------------------------------------------
 // per-scene preparation kernels
 // ------------------------------------------------------------------------------------------------
-// P[(v*HW + p)*256 + half*128 + n] = sum_c W[n*ldw + col0 + c] * in[(v*C + c)*HW + p]        (fp32 math, fp16 store)
+// P[((v*4 + half*2 + n/64)*HW + p)*64 + n%64] = sum_c W[n*ldw + col0 + c] * in[(v*C + c)*HW + p]     (fp32 math, fp16 store)
+// i.e. projected channel n' = half*128 + n of texel p lives in channel group n'/64: the TMA box of the field kernel stages
+// one 128-byte row per (texel, group).
 __global__ void __launch_bounds__(256) preproject_kernel(const float* __restrict__ in, int C, int HW,
                                                          const float* __restrict__ W, int ldw, int col0, int half_sel,
                                                          __half* __restrict__ out) {
@@ -364,7 +422,7 @@ __global__ void __launch_bounds__(256) preproject_kernel(const float* __restrict
     for (int i = 0; i < 4; ++i) {
         int p = p0 + ty * 4 + i;
         if (p >= HW) continue;
-        __half* o = out + ((size_t)v * HW + p) * 256 + half_sel * 128 + n0 + tx * 4;
+        __half* o = out + (((size_t)v * 4 + half_sel * 2 + (n0 >> 6)) * HW + p) * 64 + tx * 4;
         o[0] = __float2half_rn(acc[i][0]); o[1] = __float2half_rn(acc[i][1]);
         o[2] = __float2half_rn(acc[i][2]); o[3] = __float2half_rn(acc[i][3]);
     }
@@ -503,6 +561,27 @@ __device__ __forceinline__ void bg_point_fast(const RayFast& g, float s, float f
     for (int i = 0; i < 3; ++i) lin[i] = g.o[i] + tl * g.d[i];
 }
 
+// 2x2 tap quad of F.grid_sample(bilinear, align_corners=True, padding_mode="zeros") -- same arithmetic as bilinear_taps
+// (common.cuh) but keeping the unclamped base texel: x0 in [-1, W-1], y0 in [-1, H-1]; w = {nw, ne, sw, se}, 0 when out of range.
+struct TapQuad { int x0, y0; float w[4]; };
+__device__ __forceinline__ void tap_quad(float gx, float gy, int W, int H, TapQuad& t) {
+    const float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+    const float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float fx = ix - x0f, fy = iy - y0f;
+    const float gx1 = (x0f + 1.f) - ix, gy1 = (y0f + 1.f) - iy;
+    // NaN / far-away coordinates: every tap is out of range
+    const bool inr = (ix >= -1.f) && (ix < (float)W) && (iy >= -1.f) && (iy < (float)H);
+    const int x0 = inr ? (int)x0f : -2, y0 = inr ? (int)y0f : -2;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
+    t.x0 = x0; t.y0 = y0;
+    t.w[0] = (inr & vx0 & vy0) ? gx1 * gy1 : 0.f;
+    t.w[1] = (inr & vx1 & vy0) ? fx * gy1 : 0.f;
+    t.w[2] = (inr & vx0 & vy1) ? gx1 * fy : 0.f;
+    t.w[3] = (inr & vx1 & vy1) ? fx * fy : 0.f;
+}
+
 struct PtsRow {        // 48 bytes: view-independent per-row data, computed once per tile
     float xe[3];       // point fed to the positional encoding (fg: sample point, bg: unit-sphere point)
     float tv;          // t (fg) or inverse radius s (bg)
@@ -548,7 +627,7 @@ __device__ __forceinline__ void enc_cols(const float* x, uint32_t encb, int row,
 }
 
 template <int ICH, bool DBG>
-__global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -563,10 +642,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(BAR(ENC_READY + s), kProducerWarps);        // one elected arrival per warp
-            mbar_init(BAR(ENC_FREE + s), 1);
-            mbar_init(BAR(G_READY + s), kProducerWarps);
-            mbar_init(BAR(G_FREE + s), 1);                         // tcgen05.commit after the layer-0 MMAs that read the slot
+            mbar_init(BAR(ENC_FREE + s), 1);                      // tcgen05.commit after the layer-0 / skip MMAs that read the slot
+            mbar_init(BAR(CNT_READY + s), 4);                     // the four window warps (one per map) posted their window counts
         }
+        for (int r = 0; r < kRing; ++r) {
+            mbar_init(BAR(WIN_FULL + r), 2);                      // expect_tx arrival (+ 8 KB of TMA bytes) and the tap-weight tile
+            mbar_init(BAR(WIN_EMPTY + r), 1);                     // tcgen05.commit after the window's MMAs
+        }
+        *reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + 36) = 0u;     // issue turn: windows acquire their ring slots in sequence order
         mbar_init(BAR(ACC_READY), 1);
         mbar_init(BAR(ACC_READY + 1), 1);
         mbar_init(BAR(H_READY), 4);
@@ -592,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                          ::"r"(sbase + SM_BIAS), "l"(P.mlp.bias), "r"((uint32_t)(BIAS_FLOATS * 4)), "r"(tbar) : "memory");
         }
         __syncthreads();
-        mbar_wait(tbar, 0, P.err, 90);
+        mbar_wait(tbar, 0, P.trap, 90);
         float* vsm = reinterpret_cast<float*>(sgen + SM_VIEWS);
         const float* vsrc = reinterpret_cast<const float*>(P.sc.views);
         for (int i = threadIdx.x; i < P.nv * 16; i += kThreads) vsm[i] = __ldg(vsrc + i);
@@ -636,9 +719,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             }
             *reinterpret_cast<uint4*>(sgen + SM_SEL + row * 128 + ((chunk ^ (row & 7)) << 4)) = z;
         }
-        ident_fill(sgen + SM_IDENT, ptid0, kProducerWarps * 32);
-        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
-        ident_ones(sgen + SM_IDENT, ptid0);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -654,12 +734,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         const int pw = warp - kProducerWarp0, ptid = threadIdx.x - kProducerWarp0 * 32;
         uint32_t ph_dir_free = 1;
         uint32_t kcount = 0;
+        uint32_t wseq = 0;            // window warps: sequence number of the job's first texel window
         long long tp_pts = 0, tp_encwait = 0, tp_geom = 0, tp_gwait = 0, tp_gather = 0, tp_bar = 0;
-        long long tp_enc_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp_gf_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp_ga_j[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tw_lds = 0, tw_red = 0, tw_loop = 0;
+        long long tw_enum = 0, tw_bar2 = 0, tw_turn = 0, tw_empty = 0, tw_body = 0, tw_n = 0, tw_lat = 0;
         TSTART();
         PtsRow* pts = reinterpret_cast<PtsRow*>(sgen + SM_PTS);
         const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
-        const size_t lat_hw = (size_t)P.sc.lat_h * P.sc.lat_w, pl_hw = (size_t)P.sc.plane_h * P.sc.plane_w;
         // View-independent world points of the 64 rows of half `hh` of tile `tile` (one thread per row).  The two dependent
         // global round trips (ray order -> ray, far, t) are hidden: producer warps 8-9, idle while warps 0-7 do the per-view
         // geometry, compute half 1 of the current tile during job (v=0,h=0) and half 0 of the NEXT tile during the last job.
@@ -689,12 +770,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             for (int v = 0; v < nv; ++v) {
                 for (int h = 0; h < 2; ++h, ++kcount) {
                     const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
-                    const uint32_t rowtab = sbase + SM_ROWTAB + slot * SLOT_TAB;
                     const uint32_t encb = sbase + SM_ENC + slot * SLOT_ENC;
                     if (v == nv - 1) {
                         // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360);
                         //      written with the LAST view so the previous tile's head MMA has long released the DIR tile ----
-                        if (h == 0) { mbar_wait<kProdSleep>(BAR(DIR_FREE), ph_dir_free, P.err, 2); ph_dir_free ^= 1; }
+                        if (h == 0) { mbar_wait<kProdSleep>(BAR(DIR_FREE), ph_dir_free, P.trap, 2); ph_dir_free ^= 1; }
                         const int dt = ptid - (kProducerWarps * 32 - 4 * 32);       // last 4 producer warps: 128 threads = 64 rows x 2
                         if (dt >= 0) {
                             const int row = dt & (kHalfPts - 1), sub = dt >> 6;      // sub warp-uniform
@@ -746,9 +826,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         }
                     }
                     // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved), thread = (sub, row) ----
-                    mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.err, 1);
-                    if (DBG) { long long t1 = clock64(); tp_enc_j[(v * 2 + h) % 8] += t1 - _t0; }
+                    mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.trap, 1);
                     TLAP(tp_encwait);
+                    const int trole = (pw == 0) ? 0 : (pw == 1) ? 1 : (pw == 6) ? 2 : -1;
+                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 0, 0);
+                    const uint32_t rowinfo = sbase + SM_ROWINFO + slot * SLOT_INFO;
                     if (ptid < 4 * kHalfPts) {
                         // sub is warp-uniform (64 consecutive threads share it): no divergence between the map / chunk variants
                         const int row = ptid & (kHalfPts - 1), sub = ptid >> 6;
@@ -759,123 +841,157 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         if (IS_BG) to_camera(vx, pr.xl, cl);
                         else { cl[0] = ce[0]; cl[1] = ce[1]; cl[2] = ce[2]; }      // foreground: the lookup point IS the encoded point
                         ce[3] = pr.tv;
-                        Taps tp;
+                        float gx, gy;
+                        int mw, mh;
                         if (sub == 0) {
-                            float gx, gy;
                             local_grid_coords(P.sc, cl, gx, gy);
-                            bilinear_taps(gx, gy, P.sc.lat_w, P.sc.lat_h, tp);
+                            mw = P.sc.lat_w; mh = P.sc.lat_h;
                         } else {
-                            const float ga = (sub == 3) ? cl[1] : cl[0];
-                            const float gb = (sub == 2) ? cl[1] : cl[2];          // xz, xy, yz
-                            bilinear_taps(ga, gb, P.sc.plane_w, P.sc.plane_h, tp);
+                            gx = (sub == 3) ? cl[1] : cl[0];
+                            gy = (sub == 2) ? cl[1] : cl[2];          // xz, xy, yz
+                            mw = P.sc.plane_w; mh = P.sc.plane_h;
                         }
-                        // tap table entry: offsets in 16-byte units (texel row = 512 B = [P0 | P3]), weights as half2(w,w); the eight
-                        // 16-byte chunks of a row are XOR-swizzled by the row (lanes = rows at a 128-byte stride would otherwise all hit
-                        // the same four banks: a 32-way conflict on both stores)
-                        // zeros padding, or a padding row of the tile (sample index past N / ray past the batch: its outputs are never stored)
-                        const bool dead = ((tp.w[0] == 0.f) & (tp.w[1] == 0.f) & (tp.w[2] == 0.f) & (tp.w[3] == 0.f)) |
+                        // 2x2 tap quad of grid_sample(align_corners=True, zeros): base texel (x0, y0) in [-1, W-1] x [-1, H-1] and the four
+                        // weights (0 for an out-of-range tap).  A row whose taps all fall outside -- or a padding row of the tile
+                        // (sample index past N / ray past the batch: its outputs are never stored) -- is dead: it joins no window.
+                        TapQuad tq;
+                        tap_quad(gx, gy, mw, mh, tq);
+                        const bool dead = ((tq.w[0] == 0.f) & (tq.w[1] == 0.f) & (tq.w[2] == 0.f) & (tq.w[3] == 0.f)) |
                                           (q * kTileSamples + ((h * kHalfPts + row) >> 5) >= N) | (g * kTileRays + (row & 31) >= P.n_rays);
-                        // bit 0 of the first offset: "same texel quad as the previous row" (rows are consecutive lanes; the gather
-                        // then keeps the four texels in registers).  Never set on lane 0 or after a dead row.
-                        const int pi0 = __shfl_up_sync(0xffffffffu, tp.idx[0], 1), pi1 = __shfl_up_sync(0xffffffffu, tp.idx[1], 1);
-                        const int pi2 = __shfl_up_sync(0xffffffffu, tp.idx[2], 1), pi3 = __shfl_up_sync(0xffffffffu, tp.idx[3], 1);
-                        const bool pdead = __shfl_up_sync(0xffffffffu, (int)dead, 1) != 0;
-                        const bool same = (lane > 0) & !pdead & (pi0 == tp.idx[0]) & (pi1 == tp.idx[1]) & (pi2 == tp.idx[2]) & (pi3 == tp.idx[3]);
-                        sts128(rowtab + row * 128 + (((sub * 2) ^ (row & 7)) << 4), make_uint4(dead ? 0xFFFFFFFFu : ((uint32_t)(tp.idx[0] * 32) | (same ? 1u : 0u)),
-                                                                          tp.idx[1] * 32, tp.idx[2] * 32, tp.idx[3] * 32));
-                        sts128(rowtab + row * 128 + (((sub * 2 + 1) ^ (row & 7)) << 4), make_uint4(pack_h2(tp.w[0], tp.w[0]), pack_h2(tp.w[1], tp.w[1]),
-                                                                               pack_h2(tp.w[2], tp.w[2]), pack_h2(tp.w[3], tp.w[3])));
-                        {
-                            const bool zero = (P.ablate & 2) != 0;
-                            switch (sub) {                  // warp-uniform
-                                case 0: enc_cols<ICH, 0>(ce, encb, row, zero); break;
-                                case 1: enc_cols<ICH, 1>(ce, encb, row, zero); break;
-                                case 2: enc_cols<ICH, 2>(ce, encb, row, zero); break;
-                                default: enc_cols<ICH, 3>(ce, encb, row, zero); break;
-                            }
+                        sts128(rowinfo + sub * 1024 + row * 16,
+                               make_uint4((uint32_t)tq.x0, dead ? kDeadRow : (uint32_t)tq.y0, pack_h2(tq.w[0], tq.w[1]), pack_h2(tq.w[2], tq.w[3])));
+                        switch (sub) {                  // warp-uniform
+                            case 0: enc_cols<ICH, 0>(ce, encb, row, false); break;
+                            case 1: enc_cols<ICH, 1>(ce, encb, row, false); break;
+                            case 2: enc_cols<ICH, 2>(ce, encb, row, false); break;
+                            default: enc_cols<ICH, 3>(ce, encb, row, false); break;
                         }
                     }
-                    fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
-                    mbar_arrive_warp(BAR(ENC_READY + slot), lane);
                     if (ptid >= 256 && ptid < 256 + kHalfPts) {
                         if (v == 0 && h == 0) pts_compute(t, 1, ptid - 256);
                         else if (v == nv - 1 && h == 1 && t + (int)gridDim.x < P.n_tiles) pts_compute(t + gridDim.x, 0, ptid - 256);
                     }
                     TLAP(tp_geom);
-                    asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWTAB[slot] complete
+                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 1, 0);
+                    asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWINFO[slot] complete
                     TLAP(tp_bar);
-                    // ---- gather: one pass, 16 taps x 512 B per row; lanes 0-15 carry the layer-0 half, 16-31 the layer-3 half ----
-                    {
-                        const uint4* mapbase[4];
-                        mapbase[0] = reinterpret_cast<const uint4*>(P.mlp.plocal + (size_t)v * lat_hw * 256) + lane;
-#pragma unroll
-                        for (int m = 1; m < 4; ++m)
-                            mapbase[m] = reinterpret_cast<const uint4*>(P.mlp.pplane[m - 1] + (size_t)v * pl_hw * 256) + lane;
-                        mbar_wait<kProdSleep>(BAR(G_FREE + slot), use ^ 1, P.err, 3);
-                        if (DBG) { long long t1 = clock64(); tp_gf_j[(v * 2 + h) % 8] += t1 - _t0; }
-                        TLAP(tp_gwait);
-                        // G0 / G3 tiles are B operands of the transpose-accumulate MMA: SW128 K-major, 2 slabs of 64 rows x 128 B (64 channels)
-                        const uint32_t gdst = sbase + ((lane < 16) ? SM_G0 : SM_G3) + slot * SLOT_G + ((lane & 15) >> 3) * 8192;
-                        const uint32_t gchunk = lane & 7;
-                        // Each warp takes CONTIGUOUS rows: consecutive rows are neighbouring pixels of the 8x4 ray block at the same
-                        // sample index, which land in the same bilinear texel quad most of the time (a 64-point job touches ~4
-                        // distinct quads per plane, ~20 in the latent image).  A row whose quad equals the previous row's keeps the
-                        // 4 texels in registers instead of re-reading 2 KB through L1 (the gather's bound: 512 KB per job before).
-                        const int r_begin = (pw * kHalfPts) / kProducerWarps, r_end = ((pw + 1) * kHalfPts) / kProducerWarps;
-                        uint4 val[16];
-#pragma unroll 1
-                        for (int r = r_begin; r < r_end; ++r) {
-                            // the whole 128-byte row table in two batches of independent loads (one shared-memory round trip each,
-                            // the second hidden behind the texel loads) instead of eight dependent ones
-                            uint4 off[4];
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) off[m] = lds128(rowtab + r * 128 + (((m * 2) ^ (r & 7)) << 4));
-                            bool live[4];
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) {
-                                live[m] = off[m].x != 0xFFFFFFFFu && !(P.ablate & 1);      // warp-uniform: out-of-range lookups contribute exact zeros
-                                const bool reuse = (off[m].x & 1u) && r > r_begin && !(P.ablate & 8);
-                                if (live[m] && !reuse) {
-                                    val[m * 4 + 0] = __ldg(mapbase[m] + (off[m].x & ~1u));
-                                    val[m * 4 + 1] = __ldg(mapbase[m] + off[m].y);
-                                    val[m * 4 + 2] = __ldg(mapbase[m] + off[m].z);
-                                    val[m * 4 + 3] = __ldg(mapbase[m] + off[m].w);
-                                }
-                            }
-                            uint4 wq[4];
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) wq[m] = lds128(rowtab + r * 128 + (((m * 2 + 1) ^ (r & 7)) << 4));
-                            __half2 a0 = __floats2half2_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) {
-                                if (live[m]) {
-                                    const uint32_t wv[4] = {wq[m].x, wq[m].y, wq[m].z, wq[m].w};
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const __half2 w = *reinterpret_cast<const __half2*>(&wv[k]);
-                                        const uint4& x = val[m * 4 + k];
-                                        a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.x), a0);
-                                        a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.y), a1);
-                                        a2 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.z), a2);
-                                        a3 = __hfma2(w, *reinterpret_cast<const __half2*>(&x.w), a3);
-                                    }
-                                }
-                            }
-                            sts128(gdst + r * 128 + ((gchunk ^ (uint32_t)(r & 7)) << 4), make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
-                                                              *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3)));
-                        }
-                        fence_proxy_async();                   // the tensor core (async proxy) reads the G tiles
-                        mbar_arrive_warp(BAR(G_READY + slot), lane);
-                        if (DBG) { long long t1 = clock64(); tp_ga_j[(v * 2 + h) % 8] += t1 - _t0; }
-                        TLAP(tp_gather);
+                    if (DBG && trole >= 0 && lane == 0) { const uint4 dm = lds128(rowinfo); TRACE(trole, kcount, 2, dm.x); }
+                    // ---- texel windows: producer warps 0, 2, 4, 6 own map 0..3.  Each row's 2x2 quad lies inside exactly one 4x4 box
+                    //      of the lattice anchored at the job's minimum base texel with pitch 3, so the job's rows fall into a handful
+                    //      of boxes; per distinct box one TMA load stages the 4x4x256-channel window and the lanes scatter their rows'
+                    //      four weights into its [64 points x 16 texels] tile (rows of other boxes: zeros). ----
+                    uint4 ra = make_uint4(0u, kDeadRow, 0u, 0u), rb = ra;
+                    if (pw < 8 && (pw & 1) == 0) {
+                        ra = lds128(rowinfo + (pw >> 1) * 1024 + lane * 16);
+                        rb = lds128(rowinfo + (pw >> 1) * 1024 + (lane + 32) * 16);
                     }
+                    if (DBG) { if (ra.y != 0x12345u || rb.y != 0x54321u) TLAP(tw_lds); }
+                    fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
+                    TLAP(tw_red);
+                    mbar_arrive_warp(BAR(ENC_READY + slot), lane);
+                    TLAP(tw_loop);
+                    if (pw < 8 && (pw & 1) == 0) {
+                        const int m = pw >> 1;
+                        const bool la = ra.y != kDeadRow, lb = rb.y != kDeadRow;
+                        const int xa = (int)ra.x, ya = (int)ra.y, xb = (int)rb.x, yb = (int)rb.y;
+                        const int xm = __reduce_min_sync(0xffffffffu, min(la ? xa : 0x7fffffff, lb ? xb : 0x7fffffff));
+                        const int ym = __reduce_min_sync(0xffffffffu, min(la ? ya : 0x7fffffff, lb ? yb : 0x7fffffff));
+                        const int ka = la ? ((((ya - ym) / 3) << 16) | ((xa - xm) / 3)) : -1;
+                        const int kb = lb ? ((((yb - ym) / 3) << 16) | ((xb - xm) / 3)) : -1;
+                        // pass 1: number the distinct boxes (ca / cb = window index of this lane's rows)
+                        int nwin = 0, ca = -1, cb = -1;
+                        {
+                            bool pa = la, pb = lb;
+                            while (true) {
+                                const unsigned ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
+                                if (!(ba | bb)) break;
+                                const int key = ba ? __shfl_sync(0xffffffffu, ka, __ffs(ba) - 1) : __shfl_sync(0xffffffffu, kb, __ffs(bb) - 1);
+                                if (pa && ka == key) { ca = nwin; pa = false; }
+                                if (pb && kb == key) { cb = nwin; pb = false; }
+                                ++nwin;
+                            }
+                        }
+                        // publish the count BEFORE waiting for ring slots (a job may need more windows than the ring holds: the MMA warp
+                        // consumes them as they arrive).  Sequence numbers are handed out in map order (latent, xz, xy, yz) so that the
+                        // fp32 accumulation order of a point's windows -- and with it every output bit -- is the same on every run.
+                        volatile uint32_t* cntw = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + slot * 16);
+                        if (lane == 0) cntw[m] = (uint32_t)nwin;
+                        TLAP(tw_enum);
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        TLAP(tw_bar2);
+                        if (DBG) tw_n += nwin;
+                        const uint32_t c0 = cntw[0], c1 = cntw[1], c2 = cntw[2], c3 = cntw[3];
+                        if (trole >= 0 && lane == 0) TRACE(trole, kcount, 3, c0);
+                        const uint32_t seq0 = wseq + (m > 0 ? c0 : 0u) + (m > 1 ? c1 : 0u) + (m > 2 ? c2 : 0u);
+                        wseq += c0 + c1 + c2 + c3;
+                        if (lane == 0) mbar_arrive(BAR(CNT_READY + slot));
+                        const CUtensorMap* tm = &P.mlp.tmap[m];
+                        // Ring slots must be acquired in sequence order: a parity wait is only unambiguous while the waiter is at most
+                        // one phase ahead of the barrier, so window s may wait for its slot only after window s - kRing holds it.  The four
+                        // window warps therefore take turns (enumeration above runs in parallel; issuing is ~100 cycles per window).
+                        volatile uint32_t* turn = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + 36);
+                        if (nwin > 0) {
+                            if (lane == 0) {
+                                uint32_t spins = 0;
+                                while (*turn != seq0) {
+                                    __nanosleep(40);
+                                    if (++spins > 0x1000000u) mbar_timeout(P.trap, 4, (uint32_t)seq0, *turn);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        TLAP(tw_turn);
+                        if (trole >= 0 && lane == 0) { TRACE(trole, kcount, 4, 0); TRACE(trole, kcount, 6, nwin); if (DBG && blockIdx.x == 0 && kcount < (uint32_t)kTraceJobs) P.dbg[(size_t)gridDim.x * kDbgStride + trole * 1024 + kcount * 8 + 7] = nwin; }
+                        for (int i = 0; i < nwin; ++i) {
+                            const unsigned qa = __ballot_sync(0xffffffffu, ca == i), qb = __ballot_sync(0xffffffffu, cb == i);
+                            const int key = qa ? __shfl_sync(0xffffffffu, ka, __ffs(qa) - 1) : __shfl_sync(0xffffffffu, kb, __ffs(qb) - 1);
+                            const int ox = xm + 3 * (key & 0xffff), oy = ym + 3 * (key >> 16);
+                            const uint32_t seq = seq0 + (uint32_t)i, rs = seq % kRing, rpar = (seq / kRing) & 1u;
+                            if (lane == 0) {
+                                mbar_wait<kProdSleep>(BAR(WIN_EMPTY + rs), rpar ^ 1u, P.trap, 3);
+                                TLAP(tw_empty);
+                                mbar_expect_tx(BAR(WIN_FULL + rs), WIN_BYTES);
+                                tma_load_window(sbase + SM_WIN + rs * WIN_BYTES, tm, ox, oy, v * 4, BAR(WIN_FULL + rs));
+                            }
+                            __syncwarp();
+                            const uint32_t wt = sbase + SM_WT + rs * WT_BYTES;
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                const int r = lane + 32 * rr;
+                                const bool mine = (rr ? cb : ca) == i;
+                                const uint4 ri = rr ? rb : ra;
+                                // the 16 texel slots of the window, one 64-bit word per window row: the quad's top pair sits in window
+                                // row by at columns bx, bx+1, the bottom pair in row by+1
+                                const int bx = mine ? (int)ri.x - ox : 0, by = mine ? (int)ri.y - oy : 0;
+                                const unsigned long long top = ((unsigned long long)ri.z) << (16 * bx), bot = ((unsigned long long)ri.w) << (16 * bx);
+                                unsigned long long qw[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) qw[j] = !mine ? 0ull : (j == by) ? top : (j == by + 1) ? bot : 0ull;
+                                const uint32_t dst = wt + (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
+                                sts128(dst, make_uint4((uint32_t)qw[0], (uint32_t)(qw[0] >> 32), (uint32_t)qw[1], (uint32_t)(qw[1] >> 32)));
+                                sts128(dst + 128u, make_uint4((uint32_t)qw[2], (uint32_t)(qw[2] >> 32), (uint32_t)qw[3], (uint32_t)(qw[3] >> 32)));
+                            }
+                            fence_proxy_async();                   // the tensor core (async proxy) reads the weight tile
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR(WIN_FULL + rs));
+                            // the slot of window seq is held: the next window (this warp's or the next warp's) may acquire its own
+                            if (lane == 0) *turn = seq + 1u;
+                            TLAP(tw_body);
+                            if (DBG && m == 0 && i == nwin - 1 && lane == 0) {      // DBG only: TMA latency of the job's last latent window
+                                mbar_wait(BAR(WIN_FULL + rs), rpar, P.trap, 5);
+                                TLAP(tw_lat);
+                            }
+                        }
+                    }
+                    TLAP(tp_gather);
+                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 5, 0);
                 }
             }
         }
         if (DBG && P.dbg && ptid == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
             d[0] = tp_pts; d[1] = tp_encwait; d[2] = tp_geom; d[3] = tp_bar; d[4] = tp_gwait; d[5] = tp_gather;
-            for (int i = 0; i < 8; ++i) { d[24 + i] = tp_enc_j[i]; d[32 + i] = tp_gf_j[i]; d[48 + i] = tp_ga_j[i]; }
+            d[24] = tw_enum; d[25] = tw_bar2; d[26] = tw_turn; d[27] = tw_empty; d[28] = tw_body; d[29] = tw_n; d[30] = tw_lat; d[31] = tw_lds; d[32] = tw_red; d[33] = tw_loop;
         }
     } else if (warp == 4) {
         // =====================================================================================
@@ -884,22 +1000,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
         {
             // all 32 lanes run this loop (waits included); MMAs/commits are issued by one elected lane
             uint32_t ph_h = 0, kcount = 0;      // bit b = parity of H_READY[b]
+            uint32_t whead = 0;                 // sequence number of the next texel window to consume (the producers' ring tail runs ahead)
             long long tm_encwait = 0, tm_hwait = 0, tm_issue = 0, tm_gwait = 0;
             TSTART();
             // ENC (K-major, written by row owners) and H (MN-major = point-contiguous, written by neuron owners as 16-byte vectors)
             const uint32_t id_blk = idesc_f16(128, 32), id_blk_mn = idesc_f16(128, 32, 0, 1), id_head = idesc_f16(128, 80, 1, 0),
-                           id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16), id_half = idesc_f16(128, 64);
+                           id_q = idesc_f16(128, 64), id_rgb = idesc_f16(128, 16), id_half = idesc_f16(128, 64), id_win = idesc_f16(128, 64, 1, 0);
             const uint32_t dD = tmem + TM_D, dD3 = tmem + TM_D3, dH = tmem + TM_DH;
             const uint32_t aW0 = tmem + TM_W, aW1 = aW0 + KE / 2, aW2 = aW1 + 64, aW3h = aW2 + 64, aW3e = aW3h + 64;
             const uint32_t sH = sbase + SM_H, sDIR = sbase + SM_DIR, sWH = sbase + SM_WHEAD;
-            const uint32_t aB = tmem + TM_BIAS, sIDENT = sbase + SM_IDENT;
+            const uint32_t aB = tmem + TM_BIAS;
             const uint64_t dSEL = desc_sw128(sbase + SM_SEL);          // + 2 l: k-step l = one-hot of layer l
             auto kaddr = [](uint32_t base, int ks, uint32_t slab_bytes) { return base + (uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u; };
             // descriptor of k-step ks = base descriptor + ((ks>>2)*slab + (ks&3)*32) / 16 in the start-address field
             auto dk = [](uint64_t base, int ks, uint32_t slab_bytes) { return base + (uint64_t)(((uint32_t)(ks >> 2) * slab_bytes + (uint32_t)(ks & 3) * 32u) >> 4); };
             auto wait_h = [&](int blk, int tag) {
                 TLAP(tm_issue);
-                mbar_wait(BAR(H_READY + blk), (ph_h >> blk) & 1u, P.err, tag); ph_h ^= 1u << blk;
+                mbar_wait(BAR(H_READY + blk), (ph_h >> blk) & 1u, P.trap, tag); ph_h ^= 1u << blk;
                 TLAP(tm_hwait);
                 tc_fence_after();
             };
@@ -911,7 +1028,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             const uint32_t sQ = sH + 16384;
             auto wait_bar = [&](int b, uint32_t& ph, int tag) {
                 TLAP(tm_issue);
-                mbar_wait(BAR(b), ph, P.err, tag); ph ^= 1;
+                mbar_wait(BAR(b), ph, P.trap, tag); ph ^= 1;
                 TLAP(tm_hwait);
                 tc_fence_after();
             };
@@ -938,42 +1055,77 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                         uint64_t dENC[2], dHb[2];
                         for (int bb = 0; bb < 2; ++bb) { dENC[bb] = desc_sw128(sENC + bb * 4096); dHb[bb] = desc_mn_sw128(sHh + bb * 64, 16384, 1024); }
                         TLAP(tm_issue);
-                        mbar_wait(BAR(ENC_READY + slot), use, P.err, 10);
+                        mbar_wait(BAR(ENC_READY + slot), use, P.trap, 10);
                         TLAP(tm_encwait);
+                        if (lane == 0) TRACE(3, kcount, 0, 0);
                         tc_fence_after();
                         // Layer 0 of the whole 64-point half (N = 64): D = W0enc . ENC^T (b0 rides on the constant-one input column).
-                        // Gathered features: D += G0^T through the transpose-accumulate MMA (A = shifted identity), so the epilogue
-                        // warps never touch the gather tiles.
                         if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD, aW0 + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
                         }
                         __syncwarp();
                         TLAP(tm_issue);
-                        mbar_wait(BAR(G_READY + slot), use, P.err, 12);
-                        TLAP(tm_gwait);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t dG0 = desc_sw128(sbase + SM_G0 + slot * SLOT_G), dG3 = desc_sw128(sbase + SM_G3 + slot * SLOT_G);
-                            if (!(P.ablate & 4)) {
-#pragma unroll
-                                for (int ks = 0; ks < 8; ++ks) mma_ss(dD, desc_ident(sIDENT, ks), dk(dG0, ks, 8192), id_half, 1);
+                        mbar_wait(BAR(CNT_READY + slot), use, P.trap, 12);
+                        const volatile uint32_t* cnt = reinterpret_cast<const volatile uint32_t*>(sgen + SM_CNT + slot * 16);
+                        const uint32_t nwin = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+                        if (lane == 0) { TRACE(3, kcount, 1, nwin); if (DBG && P.dbg && blockIdx.x == 0 && kcount < (uint32_t)kTraceJobs) P.dbg[(size_t)gridDim.x * kDbgStride + 3 * 1024 + kcount * 8 + 7] = nwin; }
+                        // Bilinear lookups on the tensor pipe: per staged window, D[channel][point] += WINDOW[texel][channel]^T . TAPW[point][texel]^T
+                        // (A = the TMA-written window, MN-major: 2 channel groups of 64, 16 texels; B = the sparse tap-weight tile), and the
+                        // same for the layer-3 skip accumulator D3 from channel groups 2, 3 (model.py:142-146), which is seeded NOW together with
+                        // W3enc . ENC^T + b3 so that the ENC slot and the windows go back to the producers after layer 0, not after layer 3.
+                        auto win_a = [&](uint32_t rs, int half3) { return desc_mn_sw128(sbase + SM_WIN + rs * WIN_BYTES + half3 * 4096, 2048, 1024); };
+                        auto win_b = [&](uint32_t rs) { return desc_nosw(sbase + SM_WT + rs * WT_BYTES, 128, 256); };
+                        if (nwin <= (uint32_t)kRing) {
+                            for (uint32_t i = 0; i < nwin; ++i) {
+                                const uint32_t seq = whead + i, rs = seq % kRing;
+                                mbar_wait(BAR(WIN_FULL + rs), (seq / kRing) & 1u, P.trap, 13);
+                                tc_fence_after();
+                                if (elect_one()) mma_ss(dD, win_a(rs, 0), win_b(rs), id_win, 1);
+                                __syncwarp();
                             }
-                            tc_commit(BAR(ACC_READY));
-                            tc_commit(BAR(ACC_READY + 1));
-                            // Skip connection of layer 3 (model.py:142-146), off the critical path: its encoding and gathered parts
-                            // (and b3) are accumulated NOW into a second accumulator D3, on which layer 3 later accumulates W3h . h2 --
-                            // so the ENC and gather slots go back to the producers after layer 0 instead of after layer 3.
+                            TLAP(tm_gwait);
+                            if (elect_one()) {
+                                tc_commit(BAR(ACC_READY));
+                                tc_commit(BAR(ACC_READY + 1));
 #pragma unroll
-                            for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3, aW3e + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
-                            if (!(P.ablate & 4)) {
-#pragma unroll
-                                for (int ks = 0; ks < 8; ++ks) mma_ss(dD3, desc_ident(sIDENT, ks), dk(dG3, ks, 8192), id_half, 1);
+                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3, aW3e + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
+                                tc_commit(BAR(ENC_FREE + slot));
+                                for (uint32_t i = 0; i < nwin; ++i) {
+                                    const uint32_t rs = (whead + i) % kRing;
+                                    mma_ss(dD3, win_a(rs, 1), win_b(rs), id_win, 1);
+                                    tc_commit(BAR(WIN_EMPTY + rs));
+                                }
                             }
-                            tc_commit(BAR(ENC_FREE + slot));
-                            tc_commit(BAR(G_FREE + slot));
+                            __syncwarp();
+                        } else {
+                            // more windows than the ring holds (points spread over the source image): consume and release them one by one
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ks = 0; ks < KE / 16; ++ks) mma_ts(dD3, aW3e + ks * 8, dk(dENC[0], ks, SLAB_ENC), id_half, ks > 0);
+                                tc_commit(BAR(ENC_FREE + slot));
+                            }
+                            __syncwarp();
+                            for (uint32_t i = 0; i < nwin; ++i) {
+                                const uint32_t seq = whead + i, rs = seq % kRing;
+                                mbar_wait(BAR(WIN_FULL + rs), (seq / kRing) & 1u, P.trap, 13);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    mma_ss(dD, win_a(rs, 0), win_b(rs), id_win, 1);
+                                    mma_ss(dD3, win_a(rs, 1), win_b(rs), id_win, 1);
+                                    tc_commit(BAR(WIN_EMPTY + rs));
+                                }
+                                __syncwarp();
+                            }
+                            TLAP(tm_gwait);
+                            if (elect_one()) {
+                                tc_commit(BAR(ACC_READY));
+                                tc_commit(BAR(ACC_READY + 1));
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
+                        whead += nwin;
+                        if (lane == 0) TRACE(3, kcount, 2, 0);
                         for (int l = 1; l <= 3; ++l) {
                             const uint32_t aW = (l == 1) ? aW1 : (l == 2 ? aW2 : aW3h);
                             for (int bb = 0; bb < 2; ++bb) {
@@ -989,8 +1141,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             }
                             if (pend && v == 0 && h == 0 && l < 3) color_stage(l - 1);
                         }
+                        if (lane == 0) TRACE(3, kcount, 3, 0);
                         wait_h(0, 13);                              // h3 of both blocks written
                         wait_h(1, 13);
+                        if (lane == 0) TRACE(3, kcount, 4, 0);
                     }
                     // the previous tile's colour head (drained during this tile's first job) has left the head accumulator
                     if (v == 0 && pend) { wait_bar(HEAD_DONE, ph_done, 17); pend = false; }
@@ -1044,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
             const int rid = P.ray_order ? P.ray_order[min(slot_r, P.n_rays - 1)] : min(slot_r, P.n_rays - 1);
             const long long gp = (long long)rid * N + min(s, N - 1);
             if (stage == 0) {
-                mbar_wait(BAR(HEAD_READY), ph_head, P.err, 26); ph_head ^= 1;
+                mbar_wait(BAR(HEAD_READY), ph_head, P.trap, 26); ph_head ^= 1;
                 tc_fence_after();
                 uint32_t r[80];
 #pragma unroll
@@ -1063,7 +1217,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 }
                 tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
             } else if (stage == 1) {
-                mbar_wait(BAR(CH_READY), ph_ch, P.err, 27); ph_ch ^= 1;
+                mbar_wait(BAR(CH_READY), ph_ch, P.trap, 27); ph_ch ^= 1;
                 tc_fence_after();
                 uint32_t r[64];
 #pragma unroll
@@ -1079,7 +1233,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                 }
                 tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
             } else {
-                mbar_wait(BAR(CH_READY), ph_ch, P.err, 28); ph_ch ^= 1;
+                mbar_wait(BAR(CH_READY), ph_ch, P.trap, 28); ph_ch ^= 1;
                 tc_fence_after();
                 uint32_t r[16];
                 tmem_ld16(lane_base + TM_DH + 64, r);
@@ -1111,7 +1265,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const Params P) {
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
                             uint32_t r[32];
                             TLAP(te_work);
-                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.err, 20 + l); ph_acc ^= 1u << bb;
+                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.trap, 20 + l); ph_acc ^= 1u << bb;
                             if (DBG) { long long t1 = clock64(); te_acc_l[l * 2 + bb] += t1 - _t0; }
                             TLAP(te_accwait);
                             tc_fence_after();
@@ -1294,17 +1448,122 @@ __global__ void __launch_bounds__(128, 1) selftest_transpose_kernel(const float*
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// self-test of the texel-window MMA: one TMA box (64 ch x 4 x 4 texels x 4 groups, 128B swizzle) staged as the MN-major A operand,
+// a [64 points x 16 texels] no-swizzle K-major tap-weight tile as B:  out0 / out3 [channel][point] = sum_k win[k][channel (+128)] wt[point][k]
+__global__ void __launch_bounds__(128, 1) selftest_window_kernel(const __grid_constant__ CUtensorMap tmap, int ox, int oy,
+                                                                 const float* __restrict__ wt, float* __restrict__ out0,
+                                                                 float* __restrict__ out3, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sWin = sbase, sWt = sbase + WIN_BYTES, bar = sbase + WIN_BYTES + WT_BYTES, bar2 = bar + 8;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(sgen + WIN_BYTES + WT_BYTES + 16);
+    const int warp = threadIdx.x >> 5, c = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(sbase + WIN_BYTES + WT_BYTES + 16, 512);
+    for (int e = threadIdx.x; e < 64 * 16; e += 128) {
+        const int r = e / 16, k = e % 16;
+        *reinterpret_cast<__half*>(sgen + WIN_BYTES + (r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2) = __float2half_rn(wt[e]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, WIN_BYTES);
+        tma_load_window(sWin, &tmap, ox, oy, 0, bar);
+    }
+    mbar_wait(bar, 0, err, 96);
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        mma_ss(tmem + 0, desc_mn_sw128(sWin, 2048, 1024), desc_nosw(sWt, 128, 256), idesc_f16(128, 64, 1, 0), 0);
+        mma_ss(tmem + 64, desc_mn_sw128(sWin + 4096, 2048, 1024), desc_nosw(sWt, 128, 256), idesc_f16(128, 64, 1, 0), 0);
+        tc_commit(bar2);
+    }
+    mbar_wait(bar2, 0, err, 95);
+    tc_fence_after();
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int cb = 0; cb < 2; ++cb) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) out0[c * 64 + cb * 32 + i] = __uint_as_float(r[i]);
+        tmem_ld32(lane_base + 64 + cb * 32, r);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) out3[c * 64 + cb * 32 + i] = __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+__global__ void selftest_group_kernel(const float* __restrict__ in, int HW, __half* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= HW * 256) return;
+    const int p = idx / 256, ch = idx % 256;
+    out[((size_t)(ch >> 6) * HW + p) * 64 + (ch & 63)] = __float2half_rn(in[idx]);
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static long long* g_dbg = nullptr;   // diagnostics only (neo_tc_debug); reset by every scene creation
+static int* g_trap_host = nullptr;   // host-mapped int[8] written by mbar_timeout before a protocol trap
+static int* g_trap_dev = nullptr;
+
+static int trap_buffer() {
+    if (g_trap_host) return NEO_OK;
+    void* h = nullptr;
+    NEO_CUDA(cudaHostAlloc(&h, 8 * sizeof(int), cudaHostAllocMapped));
+    memset(h, 0, 8 * sizeof(int));
+    void* dptr = nullptr;
+    NEO_CUDA(cudaHostGetDevicePointer(&dptr, h, 0));
+    g_trap_host = (int*)h;
+    g_trap_dev = (int*)dptr;
+    return NEO_OK;
+}
+const char* tc_trap_info() {
+    static char buf[256];
+    if (!g_trap_host || g_trap_host[0] == 0) return "";
+    volatile int* t = g_trap_host;
+    snprintf(buf, sizeof(buf), " [TC field kernel: mbarrier wait timed out: tag %d, CTA %d of %d, thread %d (warp %d), barrier smem 0x%x (index %d), parity %d]",
+             t[0] - 1000, t[1], t[5], t[2], t[2] / 32, (unsigned)t[3], ((unsigned)t[3] % 1024u - (tc::SM_BAR % 1024u)) / 8, t[4]);
+    return buf;
+}
+
+// 4-D TMA descriptor over a projected map [nv*4 + group][H][W][64] fp16: box = 64 channels x 4 x 4 texels x 4 groups, 128B swizzle
+// (the field kernel's MN-major A operand), zero fill outside the map.  The driver entry point is fetched through the runtime so
+// the library links against cudart only.
+static int make_window_tmap(CUtensorMap* out, void* base, int W, int H, int nv) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        NEO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from this driver"); return NEO_ERR_UNSUPPORTED; }
+        encode = reinterpret_cast<EncodeTiled>(fn);
+    }
+    const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nv * 4};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)128 * W, (cuuint64_t)128 * W * H};
+    const cuuint32_t box[4] = {64, 4, 4, 4}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %d map", (int)r, W, H); return NEO_ERR_CUDA; }
+    return NEO_OK;
+}
+
 int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
     using namespace tc;
     const NeoSceneDesc& d = sc->desc;
     State* st = new State();
     sc->tc_state = st;
-    const int lat_hw = d.lat_h * d.lat_w, pl_hw = d.plane_h * d.plane_w;
+    g_dbg = nullptr;
     const float* planes[3] = {d.planes_xz, d.planes_xy, d.planes_yz};
     for (int i = 0; i < 4; ++i) {
         const NeoMLPParams& p = mlps[i];
@@ -1330,22 +1589,19 @@ int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
         NEO_LAUNCH_CHECK("head_kernel");
         m.headimg = (const uint4*)hb;
         m.bias = (const float*)bb;
-        // pre-projected feature maps [P0 | P3]
-        void* pl = nullptr;
-        if ((rc = scene_alloc_bytes(sc, &pl, (size_t)d.nv * lat_hw * 256 * 2))) return rc;
-        m.plocal = (const __half*)pl;
-        dim3 gl((lat_hw + 63) / 64, 2, d.nv);
-        preproject_kernel<<<gl, 256, 0, s>>>(d.latent, kLocalCh, lat_hw, p.w0, in_dim, m.enc_dim, 0, (__half*)pl);
-        preproject_kernel<<<gl, 256, 0, s>>>(d.latent, kLocalCh, lat_hw, p.w3, 128 + in_dim, 128 + m.enc_dim, 1, (__half*)pl);
-        NEO_LAUNCH_CHECK("preproject_kernel(local)");
-        for (int k = 0; k < 3; ++k) {
+        // pre-projected feature maps [P0 | P3], stored as 64-channel groups [nv*4 + group][H][W][64] + their TMA descriptors
+        const float* srcs[4] = {d.latent, planes[0], planes[1], planes[2]};
+        for (int k = 0; k < 4; ++k) {
+            const int C = k ? kWorldCh : kLocalCh, mh = k ? d.plane_h : d.lat_h, mw = k ? d.plane_w : d.lat_w, hw = mh * mw;
+            const int col = m.enc_dim + (k ? kLocalCh : 0);
             void* pp = nullptr;
-            if ((rc = scene_alloc_bytes(sc, &pp, (size_t)d.nv * pl_hw * 256 * 2))) return rc;
-            m.pplane[k] = (const __half*)pp;
-            dim3 gp((pl_hw + 63) / 64, 2, d.nv);
-            preproject_kernel<<<gp, 256, 0, s>>>(planes[k], kWorldCh, pl_hw, p.w0, in_dim, m.enc_dim + kLocalCh, 0, (__half*)pp);
-            preproject_kernel<<<gp, 256, 0, s>>>(planes[k], kWorldCh, pl_hw, p.w3, 128 + in_dim, 128 + m.enc_dim + kLocalCh, 1, (__half*)pp);
-            NEO_LAUNCH_CHECK("preproject_kernel(plane)");
+            if ((rc = scene_alloc_bytes(sc, &pp, (size_t)d.nv * hw * 256 * 2))) return rc;
+            m.pmap[k] = (const __half*)pp;
+            dim3 gp((hw + 63) / 64, 2, d.nv);
+            preproject_kernel<<<gp, 256, 0, s>>>(srcs[k], C, hw, p.w0, in_dim, col, 0, (__half*)pp);
+            preproject_kernel<<<gp, 256, 0, s>>>(srcs[k], C, hw, p.w3, 128 + in_dim, 128 + col, 1, (__half*)pp);
+            NEO_LAUNCH_CHECK("preproject_kernel");
+            if ((rc = make_window_tmap(&m.tmap[k], pp, mw, mh, d.nv))) return rc;
         }
     }
     return NEO_OK;
@@ -1355,20 +1611,18 @@ void tc_scene_free(NeoScene* sc) {
     if (sc && sc->tc_state) { delete reinterpret_cast<tc::State*>(sc->tc_state); sc->tc_state = nullptr; }
 }
 
-static long long* g_dbg = nullptr;   // set by neo_tc_debug
-static int g_ablate = 0;             // set by neo_tc_ablate (debug)
 
 int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, const float* t, int N, int mlp_index,
                     float* rgb, float* sigma, cudaStream_t s) {
     using namespace tc;
     if (!(sc->precision_mask & (1 << NEO_PREC_TC)) || !sc->tc_state) { set_error("scene was not prepared for NEO_PREC_TC"); return NEO_ERR_INVALID; }
     const State* st = reinterpret_cast<const State*>(sc->tc_state);
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        NEO_CUDA(cudaGetDevice(&dev));
-        NEO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static int n_sm_of[64] = {0};          // per device: a process may drive several GPUs
+    int dev = 0;
+    NEO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return NEO_ERR_UNSUPPORTED; }
+    if (!n_sm_of[dev]) NEO_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int n_sm = n_sm_of[dev];
     Params P;
     P.rays_o = rays->rays_o; P.rays_d = rays->rays_d; P.viewdirs = rays->viewdirs; P.far = far; P.tvals = t;
     P.ray_order = rays->ray_order;
@@ -1382,8 +1636,9 @@ int launch_field_tc(const NeoScene* sc, const NeoRays* rays, const float* far, c
     P.sc = sc->dev;
     P.mlp = st->mlp[mlp_index];
     P.rgb_out = rgb; P.sigma_out = sigma; P.err = sc->err_flag;
+    { int rc0 = trap_buffer(); if (rc0) return rc0; }
+    P.trap = g_trap_dev;
     P.dbg = g_dbg;
-    P.ablate = g_ablate;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
     const size_t smem = SM_TOTAL + 1024;
     auto launch = [&](auto kern) -> int {
@@ -1424,6 +1679,28 @@ extern "C" int neo_tc_selftest_transpose(const float* X, float* outa, float* out
     NEO_LAUNCH_CHECK("selftest_transpose_kernel");
     return NEO_OK;
 }
+// texels (H*W, 256) fp32 texel-major, wt (64,16) fp32 -> out0 / out3 (128,64): the bilinear-blend MMA of one 4x4 window at (ox, oy)
+extern "C" int neo_tc_selftest_window(const float* texels, int H, int W, int ox, int oy, const float* wt, float* out0, float* out3,
+                                      void* stream) {
+    using namespace neo;
+    if (H < 1 || W < 1 || !texels || !wt || !out0 || !out3) { set_error("neo_tc_selftest_window: bad arguments"); return NEO_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    __half* grouped = nullptr;
+    NEO_CUDA(cudaMalloc(&grouped, (size_t)H * W * 256 * sizeof(__half)));
+    tc::selftest_group_kernel<<<(H * W * 256 + 255) / 256, 256, 0, s>>>(texels, H * W, grouped);
+    alignas(64) CUtensorMap tm;
+    int rc = make_window_tmap(&tm, grouped, W, H, 1);
+    if (rc == NEO_OK) {
+        const size_t smem = tc::WIN_BYTES + tc::WT_BYTES + 64 + 1024;
+        cudaFuncSetAttribute(tc::selftest_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc::selftest_window_kernel<<<1, 128, smem, s>>>(tm, ox, oy, wt, out0, out3, nullptr);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "selftest_window_kernel");
+    }
+    cudaFree(grouped);
+    return rc;
+}
 extern "C" int neo_tc_enc_column(int in_ch, int col) {
     using namespace neo::tc;
     if ((in_ch != 3 && in_ch != 4) || col < 0 || col >= (in_ch == 3 ? 64 : 96)) return -3;
@@ -1432,6 +1709,5 @@ extern "C" int neo_tc_enc_column(int in_ch, int col) {
     if (e.kind == 0) return -2;
     return (in_ch == 3) ? enc_col_ref_index<3>(col) : enc_col_ref_index<4>(col);
 }
+extern "C" const char* neo_tc_trap_info(void) { return neo::tc_trap_info(); }
 extern "C" int neo_tc_debug(long long* buf) { neo::g_dbg = buf; return NEO_OK; }
-// Debug: sensitivity experiments -- the kernel skips parts of its work (results become wrong!): see Params::ablate.
-extern "C" int neo_tc_ablate(int mask) { neo::g_ablate = mask; return NEO_OK; }

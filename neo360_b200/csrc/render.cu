@@ -148,6 +148,7 @@ extern "C" int neo_render_fwd(const NeoScene* sc, const NeoRays* rays, const Neo
     return NEO_OK;
 }
 
+namespace neo { const char* tc_trap_info(); }
 extern "C" int neo_check_async(const NeoScene* sc, void* stream) {
     if (!sc) { set_error("null scene"); return NEO_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;

@@ -122,6 +122,14 @@ extern "C" int neo_scene_create(const NeoSceneDesc* d, const NeoMLPParams mlps[4
         set_error("neo_scene_create: feature maps must be at least 2x2");
         return NEO_ERR_INVALID;
     }
+    if (d->img_w <= 0 || d->img_h <= 0) {
+        set_error("neo_scene_create: img_w / img_h must be positive (got %d x %d)", d->img_w, d->img_h);
+        return NEO_ERR_INVALID;
+    }
+    if (!d->planes_xz || !d->planes_xy || !d->planes_yz || !d->latent || !d->src_poses || !d->src_focal || !d->src_c) {
+        set_error("neo_scene_create: null feature map / camera pointer");
+        return NEO_ERR_INVALID;
+    }
     if (!(precision_mask & ((1 << NEO_PREC_FP32) | (1 << NEO_PREC_TC)))) {
         set_error("neo_scene_create: empty precision mask");
         return NEO_ERR_INVALID;

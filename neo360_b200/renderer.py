@@ -108,18 +108,38 @@ class NeRF_TP(nn.Module):
         self.fg_coarse_mlp, self.fg_fine_mlp = mk(3), mk(3)
         self.bg_coarse_mlp, self.bg_fine_mlp = mk(4), mk(4)
         self._scene: Optional[Scene] = None
-        self._scene_key = None
+        self._scene_src = None          # (tensors, versions) the scene was built from: compared by identity, never by address
+        self._scene_inputs = None       # arguments of the last set_scene (to re-pack when the parameters change)
+        self._param_key = None
         self._ws = None
 
     # ---- scene handling (encoder hoisted, quirk Q5) ----
     def _mlps(self):
         return [self.fg_coarse_mlp, self.bg_coarse_mlp, self.fg_fine_mlp, self.bg_fine_mlp]
 
+    def _params_version(self):
+        """Identity of the packed weights: every parameter's storage and in-place version (optimizer steps, load_state_dict)."""
+        return tuple((p.data_ptr(), p._version) for m in self._mlps() for p in m.parameters())
+
     def set_scene(self, planes_xz, planes_xy, planes_yz, latent, src_poses, src_focal, src_c, img_wh, precisions=None):
+        """Build the per-scene state (pre-projected feature maps, cameras, packed weights).  The scene snapshots the CURRENT
+        parameters; `forward` re-packs it when they have changed since (training steps, load_state_dict)."""
         lib = L.load()
         dev = planes_xz.device
         if dev.type != "cuda":
             raise RuntimeError("neo360_b200 needs CUDA tensors (no CPU fallback)")
+        nv = planes_xz.shape[0]
+        if planes_xz.dim() != 4 or latent.dim() != 4:
+            raise ValueError("planes must be (NV,128,Hp,Wp) and latent (NV,512,Hl,Wl)")
+        if not (planes_xy.shape == planes_xz.shape == planes_yz.shape):
+            raise ValueError(f"tri-planes must share one shape, got {tuple(planes_xz.shape)} {tuple(planes_xy.shape)} {tuple(planes_yz.shape)}")
+        if latent.shape[0] != nv or nv != self.num_src_views:
+            raise ValueError(f"scene has {nv} plane views / {latent.shape[0]} latent views, the model was built for {self.num_src_views}")
+        if src_poses.shape[0] != nv or tuple(src_poses.shape[1:]) != (4, 4):
+            raise ValueError(f"src_poses must be ({nv},4,4), got {tuple(src_poses.shape)}")
+        if int(img_wh[0]) <= 0 or int(img_wh[1]) <= 0:
+            raise ValueError(f"img_wh must be positive, got {img_wh}")
+        self._scene_inputs = (planes_xz, planes_xy, planes_yz, latent, src_poses, src_focal, src_c, tuple(img_wh), precisions)
         keep = []
         f = lambda t: (keep.append(t.detach().contiguous().float()) or keep[-1])
         d = L.NeoSceneDesc()
@@ -135,29 +155,46 @@ class NeRF_TP(nn.Module):
         for p in precisions:
             mask |= 1 << PRECISIONS[p]
         h = C.c_void_p()
-        L.check(lib.neo_scene_create(C.byref(d), arr, mask, C.byref(h), torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(dev):
+            L.check(lib.neo_scene_create(C.byref(d), arr, mask, C.byref(h), torch.cuda.current_stream().cuda_stream))
         self._scene = Scene(h, lib.neo_scene_bytes(h))
+        self._scene.nv = nv
+        self._param_key = self._params_version()
+        self._scene_src = None
         return self._scene
+
+    def _same_source(self, tensors) -> bool:
+        """True when the scene was built from exactly these tensor OBJECTS at their current in-place versions.  Addresses are
+        not compared: the caching allocator hands a freed block back at the same address for the next scene."""
+        src = self._scene_src
+        return (src is not None and len(src[0]) == len(tensors) and all(a is b for a, b in zip(src[0], tensors))
+                and src[1] == tuple(t._version for t in tensors))
 
     def _ensure_scene(self, rays):
         if all(k in rays for k in ("planes_xz", "planes_xy", "planes_yz", "latent")):
-            key = tuple((rays[k].data_ptr(), rays[k]._version) for k in ("planes_xz", "latent", "src_poses"))
-            if key != self._scene_key:
+            keyed = tuple(rays[k] for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses"))
+            if not self._same_source(keyed):
                 W, H = rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2]
                 self.set_scene(rays["planes_xz"], rays["planes_xy"], rays["planes_yz"], rays["latent"], rays["src_poses"],
                                rays["src_focal"], rays["src_c"], (W, H))
-                self._scene_key = key
+                self._scene_src = (keyed, tuple(t._version for t in keyed))
         elif self.encoder is not None and "src_imgs" in rays:
-            key = tuple((rays[k].data_ptr(), rays[k]._version) for k in ("src_imgs", "src_poses"))
-            if key != self._scene_key:
+            keyed = tuple(rays[k] for k in ("src_imgs", "src_poses", "src_focal", "src_c"))
+            if not self._same_source(keyed):
                 with torch.no_grad():
                     xz, xy, yz = self.encoder(rays["src_imgs"], rays["src_poses"], rays["src_focal"], rays["src_c"])
                     latent = self.encoder.spatial_encoder.latent
                 W, H = rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2]
                 self.set_scene(xz, xy, yz, latent, rays["src_poses"], rays["src_focal"], rays["src_c"], (W, H))
-                self._scene_key = key
+                self._scene_src = (keyed, tuple(t._version for t in keyed))
         if self._scene is None:
             raise RuntimeError("no scene: call set_scene(...) or pass planes_*/latent in `rays`, or give an encoder")
+        if self._param_key != self._params_version():
+            # the packed weights (fp32 transposes, TMEM image, W0/W3-projected feature maps) are stale: re-pack from the kept inputs
+            src = self._scene_src
+            a = self._scene_inputs
+            self.set_scene(*a[:8], precisions=a[8])
+            self._scene_src = src
         return self._scene
 
     # ---- the reference's call surface ----
@@ -224,8 +261,9 @@ class NeRF_TP(nn.Module):
             want("fg_rgb_s", n, NL, 3); want("bg_rgb_s", n, NL, 3)
             if out_depth:
                 want("fg_w", n, NL); want("bg_w", n, NL)
-        L.check(lib.neo_render_fwd(sc.handle, C.byref(r), C.byref(cfg), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
-                                   torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(dev):
+            L.check(lib.neo_render_fwd(sc.handle, C.byref(r), C.byref(cfg), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
+                                       torch.cuda.current_stream().cuda_stream))
         ret = []
         for lvl in range(2):
             if out_depth:
@@ -240,17 +278,19 @@ class NeRF_TP(nn.Module):
     def index_grid(self, samples: torch.Tensor) -> torch.Tensor:
         """encoder_tp_fusion_conv.py:122-209: samples (...,3) world -> (NV*M,128), rows ordered (view, point)."""
         pts = samples.reshape(-1, 3).contiguous().float()
-        out = torch.empty(self.num_src_views * pts.shape[0], 128, device=pts.device)
-        L.check(L.load().neo_index_grid(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
-                                        torch.cuda.current_stream().cuda_stream))
+        out = torch.empty(self._scene.nv * pts.shape[0], 128, device=pts.device)
+        with torch.cuda.device(pts.device):
+            L.check(L.load().neo_index_grid(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
+                                            torch.cuda.current_stream().cuda_stream))
         return out
 
     def get_local_feats(self, samples: torch.Tensor) -> torch.Tensor:
         """model.py:239-264: samples (...,3) world -> (NV*M,512)."""
         pts = samples.reshape(-1, 3).contiguous().float()
-        out = torch.empty(self.num_src_views * pts.shape[0], 512, device=pts.device)
-        L.check(L.load().neo_index_local(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
-                                         torch.cuda.current_stream().cuda_stream))
+        out = torch.empty(self._scene.nv * pts.shape[0], 512, device=pts.device)
+        with torch.cuda.device(pts.device):
+            L.check(L.load().neo_index_local(self._scene.handle, L.ptr(pts), pts.shape[0], L.ptr(out),
+                                             torch.cuda.current_stream().cuda_stream))
         return out
 
     def field_eval(self, rays, far, t_vals, mlp_index: int, chunk: int = 0, precision: Optional[str] = None):
@@ -264,9 +304,10 @@ class NeRF_TP(nn.Module):
         r.rays_o, r.rays_d, r.viewdirs = L.ptr(o), L.ptr(d), L.ptr(vd)
         rgb = torch.empty(n, N, 3, device=t.device)
         sig = torch.empty(n, N, 1, device=t.device)
-        L.check(L.load().neo_field_eval(self._scene.handle, C.byref(r), L.ptr(fr), L.ptr(t), N, mlp_index,
-                                        PRECISIONS[precision or self.precision], L.ptr(rgb), L.ptr(sig),
-                                        torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(t.device):
+            L.check(L.load().neo_field_eval(self._scene.handle, C.byref(r), L.ptr(fr), L.ptr(t), N, mlp_index,
+                                            PRECISIONS[precision or self.precision], L.ptr(rgb), L.ptr(sig),
+                                            torch.cuda.current_stream().cuda_stream))
         return rgb, sig
 
     def check(self):

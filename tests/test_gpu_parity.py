@@ -290,6 +290,32 @@ def test_tc_selftest_transpose(cuda):
     assert md(oa, ref) == 0.0
 
 
+def test_tc_selftest_window(cuda):
+    """Texel-window MMA (the bilinear lookups of the TC field kernel): one TMA box load of a 4x4x256-channel window (128B swizzle,
+    zero fill outside the map) as the MN-major A operand, a sparse [64 points x 16 texels] no-swizzle K-major tap-weight tile as B.
+    Exact in fp16 products / fp32 accumulation, including windows that straddle or miss the map."""
+    from neo360_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(2)
+    H, W = 6, 7
+    tex = torch.randn(H * W, 256, generator=g)
+    for ox, oy in ((1, 1), (-1, -2), (5, 4), (3, 2), (-4, 0), (0, 6)):
+        wt = torch.rand(64, 16, generator=g) * (torch.rand(64, 16, generator=g) < 0.3)
+        o0 = torch.zeros(128, 64, device=cuda)
+        o3 = torch.zeros(128, 64, device=cuda)
+        L.check(lib.neo_tc_selftest_window(L.ptr(tex.to(cuda)), H, W, ox, oy, L.ptr(wt.to(cuda)), L.ptr(o0), L.ptr(o3),
+                                           torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        win = torch.zeros(16, 256)
+        for k in range(16):
+            y, x = oy + k // 4, ox + k % 4
+            if 0 <= y < H and 0 <= x < W:
+                win[k] = tex[y * W + x]
+        ref = (wt.half().double() @ win.half().double()).T.float()          # (256, 64)
+        print("window MMA at", (ox, oy), "err", md(o0, ref[:128]), md(o3, ref[128:]))
+        assert md(o0, ref[:128]) < 1e-5 and md(o3, ref[128:]) < 1e-5
+
+
 def test_field_eval_tc_vs_oracle(cuda):
     """TC field (fp16 operands, pre-projected features, folded head) against the oracle on identical t-values.
     Stated tolerance: |rgb| 2e-2, sigma 2e-2 + 2% (fp16 operand rounding through a 6-layer gained MLP)."""
@@ -360,7 +386,10 @@ def test_vanilla_nerf_vs_reference_vectors(cuda, tag):
 
 
 def test_tc_blocked_frame_order_is_pure_scheduling(cuda):
-    """NEO_PREC_TC with NeoRays.ray_order (8x4 pixel blocks) must give bit-identical pixels to the identity order."""
+    """NEO_PREC_TC with NeoRays.ray_order (8x4 pixel blocks) against the identity order.  The ray order decides which 64 points
+    share a job and therefore how a point's texel windows are grouped, i.e. the order of its fp32 accumulation on the tensor pipe:
+    the pixels agree to accumulation rounding (stated: 1e-3 on rgb in [0,1] / depth), not bit for bit.  (Line 243 keeps the
+    bit-exact check for the fp32 CUDA-core path.)"""
     W, H, nc, nf = 48, 36, 24, 12
     net, osc, P = make_net(cuda, (W, H), (24, 32), nc, nf, 2, precisions=("tc",), precision="tc")
     pose = synth.target_pose(11, 100)
@@ -371,7 +400,7 @@ def test_tc_blocked_frame_order_is_pure_scheduling(cuda):
         b = net.render_rays_test(rays, chunk=512, img_wh=(W, H))
     net.check()
     for k in ("rgb", "fg_rgb", "bg_rgb", "depth"):
-        assert md(a[k], b[k]) == 0, k
+        assert md(a[k], b[k]) < 1e-3, k
 
 
 # ---------------- Mip-NeRF 360 (row a18) ----------------
@@ -495,9 +524,12 @@ def test_tc_randomized_and_train_tuple(cuda, golden):
 # ---------------- BASELINE.json full size (configs[1]: 640x480, 128+64 samples, 3 source views) ----------------
 
 def test_full_size_frame_properties(cuda):
-    """At the benchmark's full size the oracle takes ~1 h per frame, so parity is carried by size-independent properties:
-    (1) idempotence: two renders of the same frame are bit-identical (no race in the persistent tensor-core kernel);
-    (2) the 8x4-pixel-block schedule is pure scheduling: a 16 384-ray prefix rendered in row-major order agrees bit for bit;
+    """Whole-frame companion of test_headline_config_vs_oracle (which compares whole chunks of this frame with the oracle): at the
+    benchmark's full size the oracle takes ~1 h per frame, so the rest of the frame is covered by size-independent properties:
+    (1) idempotence: two renders of the same frame are bit-identical (no race in the persistent tensor-core kernel; texel windows
+        are accumulated in a fixed order);
+    (2) the 8x4-pixel-block schedule is pure scheduling: a 16 384-ray prefix rendered in row-major order agrees up to the fp32
+        accumulation order of each point's texel windows (stated: 1e-3);
     (3) the tensor-core path agrees with the reference-formulation fp32 CUDA path (itself within 2e-4 of the reference vectors
         at the small sizes) on those rays: L-inf <= 3e-2 on rgb and acc, PSNR >= 40 dB;
     (4) range / compositing invariants: rgb in [-1e-3, 1+1e-3]-ish after compositing, 0 <= acc <= 1 + 1e-5, depth >= 0."""
@@ -524,7 +556,7 @@ def test_full_size_frame_properties(cuda):
     net.check()
     for k in ("rgb", "fg_rgb", "bg_rgb", "depth", "fg_acc"):
         assert md(a[k], b[k]) == 0, ("not idempotent", k)
-        assert md(a[k][:n], c[k]) == 0, ("block order changed the result", k)
+        assert md(a[k][:n], c[k]) < 1e-3, ("block order changed the result", k)
     assert a["rgb"].shape == (W * H, 3) and torch.isfinite(a["rgb"]).all() and torch.isfinite(a["depth"]).all()
     assert float(a["rgb"].min()) >= -2e-3 and float(a["rgb"].max()) <= 1.0 + 2e-3
     assert float(a["fg_acc"].min()) >= 0.0 and float(a["fg_acc"].max()) <= 1.0 + 1e-5
@@ -535,3 +567,39 @@ def test_full_size_frame_properties(cuda):
     print(f"full-size tc vs fp32 (16384 rays): rgb L-inf {err:.2e}, PSNR {psnr:.1f} dB, acc L-inf {md(c['fg_acc'], f['fg_acc']):.2e}")
     assert err <= 3e-2 and psnr >= 40.0
     assert md(c["fg_acc"], f["fg_acc"]) <= 3e-2
+
+
+def test_headline_config_vs_oracle(cuda):
+    """BASELINE.json's metric config itself (640x480 frame, 128+64 samples, NV=3, chunk=1024; the bench scene): two whole
+    1024-ray chunks of the frame -- one through the image centre, one on the top rows where many lookups leave the source
+    images -- rendered through `render_rays_test(chunk=1024)` with NEO_PREC_TC and NEO_PREC_FP32 and compared with the oracle's
+    chunk loop on the same rays (models/neo360/model.py:861-907, models/interface.py:53-61).
+    Stated tolerances: fp32: L-inf 5e-4 (rgb, acc), 5e-3 depth (CDF-bracket flips), PSNR >= 70 dB;
+    TC (fp16 operands, fp32 accumulate): L-inf 1e-2 on rgb / acc, 2e-2 on depth, PSNR >= 45 dB."""
+    import bench
+    from neo360_b200 import NeRF_TP
+    sc, P = bench.build_scene_cpu()
+    W, H = bench.IMG_W, bench.IMG_H
+    net = NeRF_TP(num_coarse_samples=bench.N_COARSE, num_fine_samples=bench.N_FINE, num_src_views=bench.NV, precision="tc").eval()
+    net.load_state_dict(P)
+    net = net.to(cuda)
+    net.set_scene(*[sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")],
+                  sc["img_wh"], precisions=("tc", "fp32"))
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+    o, d = bench.frame_rays_cpu(0)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    for start in ((H // 2) * W, 3 * W):
+        rays = {"rays_o": o[start:start + bench.CHUNK].contiguous(), "rays_d": d[start:start + bench.CHUNK].contiguous(),
+                "viewdirs": d[start:start + bench.CHUNK].contiguous()}
+        with torch.no_grad():
+            ref = orc.render_chunked(rays, osc, P, bench.N_COARSE, bench.N_FINE, chunk=bench.CHUNK, lookup_impl="aten")
+            cr = {k: v.to(cuda) for k, v in rays.items()}
+            for prec, (tol_c, tol_d, db) in (("fp32", (5e-4, 5e-3, 70.0)), ("tc", (1e-2, 2e-2, 45.0))):
+                net.precision = prec
+                got = net.render_rays_test(cr, chunk=bench.CHUNK)
+                net.check()
+                e_rgb, e_acc, e_dep = md(got["rgb"], ref["comp_rgb"]), md(got["fg_acc"], ref["fg_acc"]), md(got["depth"], ref["depth"])
+                ps = orc.psnr(got["rgb"].cpu(), ref["comp_rgb"])
+                print(f"headline chunk @{start} [{prec}]: Linf rgb {e_rgb:.2e} acc {e_acc:.2e} depth {e_dep:.2e} PSNR {ps:.1f} dB")
+                assert e_rgb < tol_c and e_acc < tol_c and e_dep < tol_d and ps > db, (prec, start, e_rgb, e_acc, e_dep, ps)

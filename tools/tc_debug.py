@@ -6,7 +6,6 @@ import bench
 from neo360_b200 import NeRF_TP, _lib as L
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
-ablate = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = torch.device("cuda:0")
 sc, P = bench.build_scene_cpu()
 net = NeRF_TP(num_coarse_samples=128, num_fine_samples=64, precision="tc").eval()
@@ -17,26 +16,33 @@ rays = {"rays_o": o[:n].to(dev), "rays_d": d[:n].to(dev), "viewdirs": d[:n].to(d
 lib = L.load()
 with torch.no_grad():
     net.render_rays_test(rays, chunk=1024)
-    lib.neo_tc_ablate(ablate)
-    buf = torch.zeros(148 * 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 64 + 5 * 1024, dtype=torch.int64, device=dev)
     lib.neo_tc_debug(buf.data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.render_rays_test(rays, chunk=1024); e1.record(); torch.cuda.synchronize()
     lib.neo_tc_debug(None)
 ms = e0.elapsed_time(e1)
-b = buf.view(148, 64).double().cpu()
-names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P wait G_FREE", "P gather", "M wait ENC_READY", "M wait H_READY", "M issue",
-         "E wait ACC", "E wait G", "E work", "E head", "M wait G_READY"]
+tr = buf[148 * 64:].view(5, 128, 8).cpu()
+b = buf[:148 * 64].view(148, 64).double().cpu()
+names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P (unused)", "P windows", "M wait ENC_READY", "M wait H_READY", "M issue",
+         "E wait ACC", "E wait G", "E work", "E head", "M wait windows"]
 # counters are overwritten by each of the 4 field launches: they hold the LAST launch (bg fine, N=193)
 tiles = ((n + 31) // 32) * ((193 + 3) // 4)
 halfjobs_per_cta = tiles * 6 / 148
-lib.neo_tc_ablate(0)
-print(f"ablate={ablate}: {n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
+print(f"{n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
 for i, nm in enumerate(names):
     print(f"  {nm:18s} {b[:, i].mean() / halfjobs_per_cta:9.0f} cycles / half-job   (total {b[:, i].mean() / 1e6:8.2f} Mcyc)")
 
 jobs_per_bin = halfjobs_per_cta / 6
-for nm, off in (("E wait G by job (v*2+h)", 16), ("P wait ENC_FREE by job", 24), ("P wait G_FREE by job", 32), ("P gather by job", 48)):
-    print(f"  {nm:26s} " + " ".join(f"{b[:, off + i].mean() / jobs_per_bin:7.0f}" for i in range(6)))
+for i, nm in enumerate(["W enumerate", "W bar.sync 2", "W turn", "W wait EMPTY", "W issue+weights", "W latent windows (count)", "W TMA latency (last latent window)", "W  lds rowinfo", "W  fence.proxy.async", "W  arrive ENC_READY"]):
+    print(f"  {nm:36s} {b[:, 24 + i].mean() / halfjobs_per_cta:9.1f} per half-job")
 print("  E wait ACC by layer,block   " + " ".join(f"{b[:, 40 + i].mean() / halfjobs_per_cta:6.0f}" for i in range(8)))
+
+# event trace of CTA 0 (last launch), cycles relative to the MMA warp's first stamp
+t0 = int(tr[3, 0, 0])
+print("job | P0: encfree geom bar1 bar2 turn done nwin | P1: encfree geom bar1 | P6: bar2 turn done nwin | MMA: enc cnt win l3 end nwin")
+for j in range(int(sys.argv[2]) if len(sys.argv) > 2 else 8, int(sys.argv[3]) if len(sys.argv) > 3 else 40):
+    r = lambda role, k: int(tr[role, j, k]) - t0 if int(tr[role, j, k]) else -1
+    print(f"{j:3d} | {r(0,0):7d} {r(0,1):7d} {r(0,2):7d} {r(0,3):7d} {r(0,4):7d} {r(0,5):7d} {int(tr[0,j,7]):2d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} | "
+          f"{r(2,3):7d} {r(2,4):7d} {r(2,5):7d} {int(tr[2,j,7]):2d} | {r(3,0):7d} {r(3,1):7d} {r(3,2):7d} {r(3,3):7d} {r(3,4):7d} {int(tr[3,j,7]):2d}")
