@@ -47,6 +47,12 @@ def parse():
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="debug: skip the CPU oracle leg (and with it the parity block)")
     ap.add_argument("--no-extras", action="store_true", help="debug: skip the eager-GPU reference leg and the call-pattern variants")
+    ap.add_argument("--mode", default="frames", choices=["frames", "strong", "turntable", "train"],
+                    help="frames: BASELINE configs[1], one frame per rank (the headline, default); strong: ONE 640x480 frame split over the ranks "
+                         "+ NCCL all-gather of the pixels (models/interface.py:30-50); turntable: BASELINE configs[4], views sharded first; "
+                         "train: BASELINE configs[3], 4096-ray batches with an NCCL gradient all-reduce")
+    ap.add_argument("--views", type=int, default=100, help="turntable mode: number of target views")
+    ap.add_argument("--batch-rays", type=int, default=4096, help="train mode: rays per optimisation step over all ranks")
     return ap.parse_args()
 
 
@@ -241,6 +247,15 @@ def main():
     from neo360_b200 import NeRF_TP, _lib as L, build
     build.build()
     lib = L.load()
+
+    if args.mode != "frames":
+        import bench_modes
+        line = bench_modes.run(args, rank, world, local, dev, dist, peaks())
+        if rank == 0:
+            print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     sc, P = build_scene_cpu()
     net = NeRF_TP(num_coarse_samples=N_COARSE, num_fine_samples=N_FINE, num_src_views=NV, precision=args.precision).eval()

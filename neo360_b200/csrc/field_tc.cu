@@ -35,9 +35,19 @@
 namespace neo {
 namespace tc {
 
-constexpr int kThreads = 512;
-constexpr int kProducerWarp0 = 5;
-constexpr int kProducerWarps = 11;
+// 18 warps: 0-3 epilogue set A (block 0 + colour head), 4-7 epilogue set B (block 1), 8 MMA issue, 9-12 geometry, 13-16 texel windows
+// (one map each: latent, xz, xy, yz), 17 points + direction encoding.  Every hand-off is an mbarrier: the roles run decoupled, as far
+// ahead as their double-buffered slots and the window ring allow.  (5 warps on two of the four schedulers => 96 registers/thread.)
+#ifndef NEO_WIN_WARPS
+#define NEO_WIN_WARPS 4
+#endif
+constexpr int kMmaWarp = 8;
+constexpr int kGeomWarp0 = 9, kGeomWarps = 4;
+constexpr int kWinWarp0 = 13, kWinWarps = NEO_WIN_WARPS, kMapsPerWin = 4 / kWinWarps;
+constexpr int kMiscWarp = kWinWarp0 + kWinWarps;
+constexpr int kThreads = (kMiscWarp + 1) * 32;
+constexpr int kProducerWarp0 = 9;         // first non-consumer warp (set-up duties)
+constexpr int kProducerWarps = kMiscWarp + 1 - kProducerWarp0;
 constexpr int kTileRays = 32;
 constexpr int kTileSamples = 4;
 constexpr int kHalfPts = 64;          // producer->consumer unit: half a tile (32 rays x 2 samples) x 1 view
@@ -75,7 +85,8 @@ constexpr uint32_t TM_W = 224;      // weights: W0enc | W1 | W2 | W3h | W3enc   
 // slot-indexed barriers come in pairs (slot 0, slot 1)
 // ACC_READY / H_READY are indexed by the 32-point block (0/1) of the half-job: the two blocks ping-pong between the
 // tensor core and the epilogue warps, so MMA latency hides behind the other block's epilogue.
-enum Bar { ENC_READY = 0, ENC_FREE = 2, CNT_READY = 4, ACC_READY = 6, H_READY = 8, HEAD_READY = 10, DIR_FREE,
+enum Bar { ENC_READY = 0, ENC_FREE = 2, CNT_READY = 4, ACC_READY = 6, H_READY = 8, INFO_READY = 10, INFO_FREE = 12, PTS_READY = 14, PTS_FREE = 16,
+           DIR_READY = 18, HEAD_READY, DIR_FREE,
            Q_READY, CH_READY, HEAD_DONE,                  // colour head: q / v1 tile written, its MMA done, accumulator drained
            WIN_FULL, WIN_EMPTY = WIN_FULL + kRing, NUM_BARS = WIN_EMPTY + kRing };
 
@@ -108,16 +119,21 @@ struct Params {
 
 // back-off of the producers' slot waits (they run ahead of the tensor pipeline; see mbar_wait)
 #ifndef NEO_PROD_SLEEP_NS
-#define NEO_PROD_SLEEP_NS 100
+#define NEO_PROD_SLEEP_NS 0
 #endif
 constexpr int kProdSleep = NEO_PROD_SLEEP_NS;
 // consumer-side waits (MMA issue, epilogue): poll NEO_SPIN_POLLS times at full rate (the latency-critical hand-offs complete within
 // that), then back off so that a long wait does not flood the shared-memory / mbarrier pipe the producers' loads and stores need
+// suspend-time hint of mbarrier.try_wait (ns): the hardware parks a waiting thread for up to this long between checks of the phase;
+// with a long hint a waiter that has been parked for a while is woken late (measured: ~2 us after the phase flipped)
+#ifndef NEO_TRYWAIT_HINT_NS
+#define NEO_TRYWAIT_HINT_NS 64
+#endif
 #ifndef NEO_SPIN_POLLS
 #define NEO_SPIN_POLLS 16
 #endif
 #ifndef NEO_SPIN_SLEEP_NS
-#define NEO_SPIN_SLEEP_NS 64
+#define NEO_SPIN_SLEEP_NS 0
 #endif
 constexpr int kDbgStride = 64;
 // cycle accounting (neo_tc_debug): compiled only into the DBG instantiation of the kernel
@@ -151,7 +167,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // %3: suspend-time hint (ns); wakes on completion
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)NEO_TRYWAIT_HINT_NS) : "memory");
     return ok != 0;
 }
 // Wait on an mbarrier phase: asm loop with an in-register spin bound, so a protocol bug traps (launch failure reported by
@@ -187,7 +203,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* tr
             "@q bra NEO_WAIT_%=;\n\t"
             "mov.u32 %0, 0;\n\t"
             "NEO_DONE_%=:\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)SLEEP_NS) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)NEO_TRYWAIT_HINT_NS), "r"((uint32_t)SLEEP_NS) : "memory");
     } else {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
@@ -203,7 +219,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* tr
             "@q bra NEO_WAIT_%=;\n\t"
             "mov.u32 %0, 0;\n\t"
             "NEO_DONE_%=:\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u), "r"((uint32_t)NEO_SPIN_POLLS), "r"((uint32_t)NEO_SPIN_SLEEP_NS) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)NEO_TRYWAIT_HINT_NS), "r"((uint32_t)NEO_SPIN_POLLS), "r"((uint32_t)NEO_SPIN_SLEEP_NS) : "memory");
     }
     if (!ok) mbar_timeout(trapinfo, tag, bar, parity);
 }
@@ -641,10 +657,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(BAR(ENC_READY + s), kProducerWarps);        // one elected arrival per warp
+            mbar_init(BAR(ENC_READY + s), kGeomWarps);            // one elected arrival per geometry warp
             mbar_init(BAR(ENC_FREE + s), 1);                      // tcgen05.commit after the layer-0 / skip MMAs that read the slot
-            mbar_init(BAR(CNT_READY + s), 4);                     // the four window warps (one per map) posted their window counts
+            mbar_init(BAR(CNT_READY + s), kWinWarps);             // the window warps posted their maps' window counts
+            mbar_init(BAR(INFO_READY + s), kGeomWarps);           // ROWINFO[s] written
+            mbar_init(BAR(INFO_FREE + s), kWinWarps);             // ... and read by the window warps
+            mbar_init(BAR(PTS_READY + s), 1);                     // world points of tile half s written by the point warp
+            mbar_init(BAR(PTS_FREE + s), kGeomWarps);             // ... and no longer needed (last view done)
         }
+        mbar_init(BAR(DIR_READY), 1);
         for (int r = 0; r < kRing; ++r) {
             mbar_init(BAR(WIN_FULL + r), 2);                      // expect_tx arrival (+ 8 KB of TMA bytes) and the tap-weight tile
             mbar_init(BAR(WIN_EMPTY + r), 1);                     // tcgen05.commit after the window's MMAs
@@ -661,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         mbar_init(BAR(HEAD_DONE), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(sbase + SM_BAR + 8 * NUM_BARS, 512);
+    if (warp == kMmaWarp) tmem_alloc(sbase + SM_BAR + 8 * NUM_BARS, 512);
     {   // head weights (pre-swizzled UMMA tiles) + biases -> smem with one TMA bulk copy each (cp.async.bulk, mbarrier tx-count)
         const uint32_t tbar = BAR(NUM_BARS + 1);
         if (threadIdx.x == 0) {
@@ -708,9 +729,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         }
         tc_wait_st();
     } else if (warp >= kProducerWarp0) {
-        const int ptid0 = threadIdx.x - kProducerWarp0 * 32;
-        if (ptid0 < 256) {   // selector tile: row n (point), logical k = 17 l  <->  k-step l, element l   is 1.0
-            const int row = ptid0 >> 3, chunk = ptid0 & 7;
+        for (int e = threadIdx.x - kProducerWarp0 * 32; e < 256; e += kProducerWarps * 32) {   // selector tile: row n (point), logical k = 17 l  <->  k-step l, element l   is 1.0
+            const int row = e >> 3, chunk = e & 7;
             uint4 z = make_uint4(0u, 0u, 0u, 0u);
             if ((chunk & 1) == 0) {
                 const int l = chunk >> 1;                         // logical byte 34 l: chunk 2l, half-word l
@@ -727,120 +747,116 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
 
     const int nv = P.nv, N = P.N;
 
-    if (warp >= kProducerWarp0) {
+    if (warp == kMiscWarp) {
         // =====================================================================================
-        // PRODUCERS.  Unit of work: half-job (tile, view, half) = 64 points of one view, double-buffered slots.
+        // POINT / DIRECTION WARP.  Per tile: the view-independent world points of its two 64-row halves (two dependent global
+        // round trips: ray order -> ray, far, t) and the view-mean direction encoding of the quirk-Q1 conditioning rays.
         // =====================================================================================
-        const int pw = warp - kProducerWarp0, ptid = threadIdx.x - kProducerWarp0 * 32;
-        uint32_t ph_dir_free = 1;
-        uint32_t kcount = 0;
-        uint32_t wseq = 0;            // window warps: sequence number of the job's first texel window
-        long long tp_pts = 0, tp_encwait = 0, tp_geom = 0, tp_gwait = 0, tp_gather = 0, tp_bar = 0;
-        long long tw_lds = 0, tw_red = 0, tw_loop = 0;
-        long long tw_enum = 0, tw_bar2 = 0, tw_turn = 0, tw_empty = 0, tw_body = 0, tw_n = 0, tw_lat = 0;
-        TSTART();
         PtsRow* pts = reinterpret_cast<PtsRow*>(sgen + SM_PTS);
         const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
-        // View-independent world points of the 64 rows of half `hh` of tile `tile` (one thread per row).  The two dependent
-        // global round trips (ray order -> ray, far, t) are hidden: producer warps 8-9, idle while warps 0-7 do the per-view
-        // geometry, compute half 1 of the current tile during job (v=0,h=0) and half 0 of the NEXT tile during the last job.
-        auto pts_compute = [&](int tile, int hh, int th) {
-            const int g2 = tile / P.sg, q2 = tile % P.sg;
-            const int n = hh * kHalfPts + th, rl = n & 31, sl = n >> 5;
-            const int slot_r = min(g2 * kTileRays + rl, P.n_rays - 1);
-            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
-            const int s = min(q2 * kTileSamples + sl, N - 1);
-            const float fr = P.far[rid];
-            const float tv = P.tvals[(long long)rid * N + s];
-            RayFast rg;
-            ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
-            PtsRow pr;
-            pr.tv = tv;
-            if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
-            else {
-                for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x, ++tcount) {
+            const int g = t / P.sg, q = t % P.sg;
+            const uint32_t tpar = tcount & 1u;
+            for (int hh = 0; hh < 2; ++hh) {
+                mbar_wait<kProdSleep>(BAR(PTS_FREE + hh), tpar ^ 1u, P.trap, 6);       // the geometry warps are done with the previous tile's half
+                for (int th = lane; th < kHalfPts; th += 32) {
+                    const int n = hh * kHalfPts + th, rl = n & 31, sl = n >> 5;
+                    const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
+                    const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
+                    const int sidx = min(q * kTileSamples + sl, N - 1);
+                    const float fr = P.far[rid];
+                    const float tv = P.tvals[(long long)rid * N + sidx];
+                    RayFast rg;
+                    ray_fast(P.rays_o + 3 * rid, P.rays_d + 3 * rid, fr, rg, IS_BG);
+                    PtsRow pr;
+                    pr.tv = tv;
+                    if (IS_BG) bg_point_fast(rg, tv, P.far_unc, pr.xe, pr.xl);
+                    else {
+                        for (int i = 0; i < 3; ++i) { pr.xe[i] = rg.o[i] + tv * rg.d[i]; pr.xl[i] = pr.xe[i]; }
+                    }
+                    pts[n] = pr;
+                }
+                mbar_arrive_warp(BAR(PTS_READY + hh), lane);
             }
-            pts[n] = pr;
-        };
-        if (ptid < kHalfPts && (int)blockIdx.x < P.n_tiles) pts_compute(blockIdx.x, 0, ptid);
-        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));
-        TLAP(tp_pts);
-        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360) ----
+            mbar_wait<kProdSleep>(BAR(DIR_FREE), tpar ^ 1u, P.trap, 2);               // the previous tile's head MMA has read the DIR tile
+            for (int n = lane; n < 2 * kHalfPts; n += 32) {
+                const int rl = n & 31, sl = n >> 5;
+                const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
+                const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
+                const int sidx = min(q * kTileSamples + sl, N - 1);
+                const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
+                const int c0 = (rid / ch) * ch;
+                const int Bc = min(ch, P.n_rays - c0);
+                const long long jl = (long long)(rid - c0) * N + sidx;
+                const int src = c0 + ((jl < 0x7fffffffLL) ? (int)((unsigned)jl % (unsigned)Bc) : (int)(jl % Bc));
+                const float wd[3] = {P.viewdirs[3 * src], P.viewdirs[3 * src + 1], P.viewdirs[3 * src + 2]};
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                for (int vv = 0; vv < nv; ++vv) {
+                    float dc[3];
+                    rotate_to_camera(vxs[vv], wd, dc);
+#pragma unroll
+                    for (int e = 0; e < kDirEnc; ++e) {
+                        float val;
+                        if (e < 3) val = dc[e];
+                        else {
+                            const int q0 = e - 3;
+                            const bool shifted = q0 >= 12;
+                            const int qq = shifted ? q0 - 12 : q0;
+                            const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
+                            val = __sinf(shifted ? xb + 1.57079637f : xb);
+                        }
+                        acc[e] += val;
+                    }
+                }
+                const float inv = 1.0f / (float)nv;
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk)
+                    sts128(sbase + SM_DIR + n * 128 + ((chunk ^ (n & 7)) << 4),
+                           make_uint4(pack_h2(acc[8 * chunk] * inv, acc[8 * chunk + 1] * inv), pack_h2(acc[8 * chunk + 2] * inv, acc[8 * chunk + 3] * inv),
+                                      pack_h2(acc[8 * chunk + 4] * inv, acc[8 * chunk + 5] * inv), pack_h2(acc[8 * chunk + 6] * inv, acc[8 * chunk + 7] * inv)));
+            }
+            fence_proxy_async();
+            mbar_arrive_warp(BAR(DIR_READY), lane);
+        }
+    } else if (warp >= kGeomWarp0 && warp < kGeomWarp0 + kGeomWarps) {
+        // =====================================================================================
+        // GEOMETRY WARPS.  Unit of work: half-job (tile, view, half) = 64 points of one view; thread = (row, map pair): camera
+        // transform, the 2x2 tap quads of two maps (-> ROWINFO) and two quarters of the row's positional encoding (-> ENC).
+        // =====================================================================================
+        const int gt = threadIdx.x - kGeomWarp0 * 32, row = gt & (kHalfPts - 1), pair = gt >> 6;      // pair is warp-uniform
+        const PtsRow* pts = reinterpret_cast<const PtsRow*>(sgen + SM_PTS);
+        const ViewXform* vxs = reinterpret_cast<const ViewXform*>(sgen + SM_VIEWS);
+        uint32_t kcount = 0, tcount = 0;
+        long long tp_encwait = 0, tp_geom = 0;
+        TSTART();
+        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x, ++tcount) {
             const int g = t / P.sg, q = t % P.sg;
             for (int v = 0; v < nv; ++v) {
                 for (int h = 0; h < 2; ++h, ++kcount) {
                     const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
                     const uint32_t encb = sbase + SM_ENC + slot * SLOT_ENC;
-                    if (v == nv - 1) {
-                        // ---- mean over views of the direction encoding of the quirk-Q1 conditioning ray (model.py:357-360);
-                        //      written with the LAST view so the previous tile's head MMA has long released the DIR tile ----
-                        if (h == 0) { mbar_wait<kProdSleep>(BAR(DIR_FREE), ph_dir_free, P.trap, 2); ph_dir_free ^= 1; }
-                        const int dt = ptid - (kProducerWarps * 32 - 4 * 32);       // last 4 producer warps: 128 threads = 64 rows x 2
-                        if (dt >= 0) {
-                            const int row = dt & (kHalfPts - 1), sub = dt >> 6;      // sub warp-uniform
-                            const int n = h * kHalfPts + row, rl = n & 31, sl = n >> 5;
-                            const int slot_r = min(g * kTileRays + rl, P.n_rays - 1);
-                            const int rid = P.ray_order ? P.ray_order[slot_r] : slot_r;
-                            const int s = min(q * kTileSamples + sl, N - 1);
-                            const int ch = P.chunk > 0 ? P.chunk : P.n_rays;
-                            const int c0 = (rid / ch) * ch;
-                            const int Bc = min(ch, P.n_rays - c0);
-                            const long long jl = (long long)(rid - c0) * N + s;
-                            const int src = c0 + ((jl < 0x7fffffffLL) ? (int)((unsigned)jl % (unsigned)Bc) : (int)(jl % Bc));
-                            const float wd[3] = {P.viewdirs[3 * src], P.viewdirs[3 * src + 1], P.viewdirs[3 * src + 2]};
-                            // thread `sub` produces K columns [16 sub, 16 sub + 16) of the 32-wide (27 used) direction encoding
-                            float acc[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-                            for (int vv = 0; vv < nv; ++vv) {
-                                float dc[3];
-                                rotate_to_camera(vxs[vv], wd, dc);
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-#pragma unroll
-                                    for (int sb = 0; sb < 2; ++sb) {
-                                        const int e = sb * 16 + i;
-                                        if (sub == sb && e < kDirEnc) {
-                                            float val;
-                                            if (e < 3) val = dc[e];
-                                            else {
-                                                const int q0 = e - 3;
-                                                const bool shifted = q0 >= 12;
-                                                const int qq = shifted ? q0 - 12 : q0;
-                                                const float xb = dc[qq % 3] * (float)(1 << (qq / 3));
-                                                val = __sinf(shifted ? xb + 1.57079637f : xb);
-                                            }
-                                            acc[i] += val;
-                                        }
-                                    }
-                                }
-                            }
-                            const float inv = 1.0f / (float)nv;
-#pragma unroll
-                            for (int c2 = 0; c2 < 2; ++c2) {
-                                const int chunk = sub * 2 + c2;
-                                sts128(sbase + SM_DIR + n * 128 + ((chunk ^ (n & 7)) << 4),
-                                       make_uint4(pack_h2(acc[8 * c2] * inv, acc[8 * c2 + 1] * inv), pack_h2(acc[8 * c2 + 2] * inv, acc[8 * c2 + 3] * inv),
-                                                  pack_h2(acc[8 * c2 + 4] * inv, acc[8 * c2 + 5] * inv), pack_h2(acc[8 * c2 + 6] * inv, acc[8 * c2 + 7] * inv)));
-                            }
-                        }
-                    }
-                    // ---- per-view geometry: 4 threads per row (one map each; encoding chunks interleaved), thread = (sub, row) ----
-                    mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.trap, 1);
-                    TLAP(tp_encwait);
-                    const int trole = (pw == 0) ? 0 : (pw == 1) ? 1 : (pw == 6) ? 2 : -1;
-                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 0, 0);
                     const uint32_t rowinfo = sbase + SM_ROWINFO + slot * SLOT_INFO;
-                    if (ptid < 4 * kHalfPts) {
-                        // sub is warp-uniform (64 consecutive threads share it): no divergence between the map / chunk variants
-                        const int row = ptid & (kHalfPts - 1), sub = ptid >> 6;
-                        const PtsRow pr = pts[h * kHalfPts + row];
-                        const ViewXform vx = vxs[v];
-                        float ce[4], cl[3];
-                        to_camera(vx, pr.xe, ce);
-                        if (IS_BG) to_camera(vx, pr.xl, cl);
-                        else { cl[0] = ce[0]; cl[1] = ce[1]; cl[2] = ce[2]; }      // foreground: the lookup point IS the encoded point
-                        ce[3] = pr.tv;
+                    if (v == 0) mbar_wait<kProdSleep>(BAR(PTS_READY + h), tcount & 1u, P.trap, 7);
+                    mbar_wait<kProdSleep>(BAR(ENC_FREE + slot), use ^ 1, P.trap, 1);
+                    mbar_wait<kProdSleep>(BAR(INFO_FREE + slot), use ^ 1, P.trap, 8);
+                    TLAP(tp_encwait);
+                    if (warp == kGeomWarp0 && lane == 0) TRACE(0, kcount, 0, 0);
+                    const PtsRow pr = pts[h * kHalfPts + row];
+                    const ViewXform vx = vxs[v];
+                    float ce[4], cl[3];
+                    to_camera(vx, pr.xe, ce);
+                    if (IS_BG) to_camera(vx, pr.xl, cl);
+                    else { cl[0] = ce[0]; cl[1] = ce[1]; cl[2] = ce[2]; }      // foreground: the lookup point IS the encoded point
+                    ce[3] = pr.tv;
+                    // a padding row of the tile (sample index past N / ray past the batch: its outputs are never stored) joins no window
+                    const bool pad = (q * kTileSamples + ((h * kHalfPts + row) >> 5) >= N) | (g * kTileRays + (row & 31) >= P.n_rays);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int sub = pair * 2 + j;
                         float gx, gy;
                         int mw, mh;
                         if (sub == 0) {
@@ -852,148 +868,187 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                             mw = P.sc.plane_w; mh = P.sc.plane_h;
                         }
                         // 2x2 tap quad of grid_sample(align_corners=True, zeros): base texel (x0, y0) in [-1, W-1] x [-1, H-1] and the four
-                        // weights (0 for an out-of-range tap).  A row whose taps all fall outside -- or a padding row of the tile
-                        // (sample index past N / ray past the batch: its outputs are never stored) -- is dead: it joins no window.
+                        // weights (0 for an out-of-range tap); a row whose taps all fall outside is dead: it joins no window
                         TapQuad tq;
                         tap_quad(gx, gy, mw, mh, tq);
-                        const bool dead = ((tq.w[0] == 0.f) & (tq.w[1] == 0.f) & (tq.w[2] == 0.f) & (tq.w[3] == 0.f)) |
-                                          (q * kTileSamples + ((h * kHalfPts + row) >> 5) >= N) | (g * kTileRays + (row & 31) >= P.n_rays);
+                        const bool dead = ((tq.w[0] == 0.f) & (tq.w[1] == 0.f) & (tq.w[2] == 0.f) & (tq.w[3] == 0.f)) | pad;
                         sts128(rowinfo + sub * 1024 + row * 16,
                                make_uint4((uint32_t)tq.x0, dead ? kDeadRow : (uint32_t)tq.y0, pack_h2(tq.w[0], tq.w[1]), pack_h2(tq.w[2], tq.w[3])));
-                        switch (sub) {                  // warp-uniform
-                            case 0: enc_cols<ICH, 0>(ce, encb, row, false); break;
-                            case 1: enc_cols<ICH, 1>(ce, encb, row, false); break;
-                            case 2: enc_cols<ICH, 2>(ce, encb, row, false); break;
-                            default: enc_cols<ICH, 3>(ce, encb, row, false); break;
-                        }
                     }
-                    if (ptid >= 256 && ptid < 256 + kHalfPts) {
-                        if (v == 0 && h == 0) pts_compute(t, 1, ptid - 256);
-                        else if (v == nv - 1 && h == 1 && t + (int)gridDim.x < P.n_tiles) pts_compute(t + gridDim.x, 0, ptid - 256);
+                    if (pair == 0) { enc_cols<ICH, 0>(ce, encb, row, false); enc_cols<ICH, 1>(ce, encb, row, false); }
+                    else { enc_cols<ICH, 2>(ce, encb, row, false); enc_cols<ICH, 3>(ce, encb, row, false); }
+                    fence_proxy_async();                       // ENC is read by the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(BAR(ENC_READY + slot));
+                        mbar_arrive(BAR(INFO_READY + slot));
+                        if (v == nv - 1) mbar_arrive(BAR(PTS_FREE + h));
                     }
                     TLAP(tp_geom);
-                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 1, 0);
-                    asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32));   // ROWINFO[slot] complete
-                    TLAP(tp_bar);
-                    if (DBG && trole >= 0 && lane == 0) { const uint4 dm = lds128(rowinfo); TRACE(trole, kcount, 2, dm.x); }
-                    // ---- texel windows: producer warps 0, 2, 4, 6 own map 0..3.  Each row's 2x2 quad lies inside exactly one 4x4 box
-                    //      of the lattice anchored at the job's minimum base texel with pitch 3, so the job's rows fall into a handful
-                    //      of boxes; per distinct box one TMA load stages the 4x4x256-channel window and the lanes scatter their rows'
-                    //      four weights into its [64 points x 16 texels] tile (rows of other boxes: zeros). ----
-                    uint4 ra = make_uint4(0u, kDeadRow, 0u, 0u), rb = ra;
-                    if (pw < 8 && (pw & 1) == 0) {
-                        ra = lds128(rowinfo + (pw >> 1) * 1024 + lane * 16);
-                        rb = lds128(rowinfo + (pw >> 1) * 1024 + (lane + 32) * 16);
+                    if (warp == kGeomWarp0 && lane == 0) TRACE(0, kcount, 1, 0);
+                }
+            }
+        }
+        if (DBG && P.dbg && gt == 0) {
+            long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
+            d[1] = tp_encwait; d[2] = tp_geom;
+        }
+    } else if (warp >= kWinWarp0) {
+        // =====================================================================================
+        // WINDOW WARPS (warp w owns kMapsPerWin consecutive maps of latent, xz, xy, yz).  Each row's 2x2 quad lies inside exactly one 4x4 box
+        // of the lattice anchored at the job's minimum base texel with pitch 3, so the job's 64 rows fall into a handful of boxes;
+        // per distinct box one TMA load stages the 4x4x256-channel window and the lanes scatter their rows' four weights into its
+        // [64 points x 16 texels] tile (rows of other boxes: zeros).
+        // =====================================================================================
+        const int wi = warp - kWinWarp0;
+        uint32_t kcount = 0, wseq = 0;            // wseq: sequence number of the job's first texel window
+        long long tw_wait = 0, tw_enum = 0, tw_bar2 = 0, tw_turn = 0, tw_empty = 0, tw_body = 0, tw_n = 0;
+        TSTART();
+        volatile uint32_t* turn = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + 36);
+        const int trole = (wi == 0) ? 1 : (wi == kWinWarps - 1) ? 2 : -1;
+        struct MapRows { uint4 ra, rb; int xm, ym, ka, kb, ca, cb, nwin; };
+        for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            for (int v = 0; v < nv; ++v) {
+                for (int h = 0; h < 2; ++h, ++kcount) {
+                    const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
+                    const uint32_t rowinfo = sbase + SM_ROWINFO + slot * SLOT_INFO;
+                    mbar_wait<kProdSleep>(BAR(INFO_READY + slot), use, P.trap, 9);
+                    TLAP(tw_wait);
+                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 0, 0);
+                    MapRows mr[kMapsPerWin];
+#pragma unroll
+                    for (int mm = 0; mm < kMapsPerWin; ++mm) {
+                        const int m = kMapsPerWin * wi + mm;
+                        mr[mm].ra = lds128(rowinfo + m * 1024 + lane * 16);
+                        mr[mm].rb = lds128(rowinfo + m * 1024 + (lane + 32) * 16);
                     }
-                    if (DBG) { if (ra.y != 0x12345u || rb.y != 0x54321u) TLAP(tw_lds); }
-                    fence_proxy_async();                       // ENC / DIR are read by the tensor core (async proxy)
-                    TLAP(tw_red);
-                    mbar_arrive_warp(BAR(ENC_READY + slot), lane);
-                    TLAP(tw_loop);
-                    if (pw < 8 && (pw & 1) == 0) {
-                        const int m = pw >> 1;
-                        const bool la = ra.y != kDeadRow, lb = rb.y != kDeadRow;
-                        const int xa = (int)ra.x, ya = (int)ra.y, xb = (int)rb.x, yb = (int)rb.y;
-                        const int xm = __reduce_min_sync(0xffffffffu, min(la ? xa : 0x7fffffff, lb ? xb : 0x7fffffff));
-                        const int ym = __reduce_min_sync(0xffffffffu, min(la ? ya : 0x7fffffff, lb ? yb : 0x7fffffff));
-                        const int ka = la ? ((((ya - ym) / 3) << 16) | ((xa - xm) / 3)) : -1;
-                        const int kb = lb ? ((((yb - ym) / 3) << 16) | ((xb - xm) / 3)) : -1;
-                        // pass 1: number the distinct boxes (ca / cb = window index of this lane's rows)
-                        int nwin = 0, ca = -1, cb = -1;
-                        {
-                            bool pa = la, pb = lb;
-                            while (true) {
-                                const unsigned ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
-                                if (!(ba | bb)) break;
-                                const int key = ba ? __shfl_sync(0xffffffffu, ka, __ffs(ba) - 1) : __shfl_sync(0xffffffffu, kb, __ffs(bb) - 1);
-                                if (pa && ka == key) { ca = nwin; pa = false; }
-                                if (pb && kb == key) { cb = nwin; pb = false; }
-                                ++nwin;
-                            }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(INFO_FREE + slot));              // the rows are in registers
+                    volatile uint32_t* cntw = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + slot * 16);
+#pragma unroll
+                    for (int mm = 0; mm < kMapsPerWin; ++mm) {
+                        MapRows& r = mr[mm];
+#ifdef NEO_ABLATE_WINDOWS
+                        const bool la = false, lb = false;          // profiling experiment only: no lookups (wrong results)
+#else
+                        const bool la = r.ra.y != kDeadRow, lb = r.rb.y != kDeadRow;
+#endif
+                        const int xa = (int)r.ra.x, ya = (int)r.ra.y, xb = (int)r.rb.x, yb = (int)r.rb.y;
+                        r.xm = __reduce_min_sync(0xffffffffu, min(la ? xa : 0x7fffffff, lb ? xb : 0x7fffffff));
+                        r.ym = __reduce_min_sync(0xffffffffu, min(la ? ya : 0x7fffffff, lb ? yb : 0x7fffffff));
+                        r.ka = la ? ((((ya - r.ym) / 3) << 16) | ((xa - r.xm) / 3)) : -1;
+                        r.kb = lb ? ((((yb - r.ym) / 3) << 16) | ((xb - r.xm) / 3)) : -1;
+                        // number the distinct boxes (ca / cb = window index of this lane's rows)
+                        r.nwin = 0; r.ca = -1; r.cb = -1;
+                        bool pa = la, pb = lb;
+                        while (true) {
+                            const unsigned ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
+                            if (!(ba | bb)) break;
+                            const int key = ba ? __shfl_sync(0xffffffffu, r.ka, __ffs(ba) - 1) : __shfl_sync(0xffffffffu, r.kb, __ffs(bb) - 1);
+                            if (pa && r.ka == key) { r.ca = r.nwin; pa = false; }
+                            if (pb && r.kb == key) { r.cb = r.nwin; pb = false; }
+                            ++r.nwin;
                         }
-                        // publish the count BEFORE waiting for ring slots (a job may need more windows than the ring holds: the MMA warp
-                        // consumes them as they arrive).  Sequence numbers are handed out in map order (latent, xz, xy, yz) so that the
-                        // fp32 accumulation order of a point's windows -- and with it every output bit -- is the same on every run.
-                        volatile uint32_t* cntw = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + slot * 16);
-                        if (lane == 0) cntw[m] = (uint32_t)nwin;
-                        TLAP(tw_enum);
-                        asm volatile("bar.sync 2, 128;" ::: "memory");
-                        TLAP(tw_bar2);
-                        if (DBG) tw_n += nwin;
-                        const uint32_t c0 = cntw[0], c1 = cntw[1], c2 = cntw[2], c3 = cntw[3];
-                        if (trole >= 0 && lane == 0) TRACE(trole, kcount, 3, c0);
-                        const uint32_t seq0 = wseq + (m > 0 ? c0 : 0u) + (m > 1 ? c1 : 0u) + (m > 2 ? c2 : 0u);
-                        wseq += c0 + c1 + c2 + c3;
-                        if (lane == 0) mbar_arrive(BAR(CNT_READY + slot));
-                        const CUtensorMap* tm = &P.mlp.tmap[m];
+                        if (lane == 0) cntw[kMapsPerWin * wi + mm] = (uint32_t)r.nwin;
+                    }
+                    // publish the counts BEFORE waiting for ring slots (a job may need more windows than the ring holds: the MMA warp
+                    // consumes them as they arrive).  Sequence numbers are handed out in map order (latent, xz, xy, yz) so that the
+                    // fp32 accumulation order of a point's windows -- and with it every output bit -- is the same on every run.
+                    TLAP(tw_enum);
+                    asm volatile("bar.sync 2, %0;" ::"r"(kWinWarps * 32) : "memory");
+                    const uint32_t c0 = cntw[0], c1 = cntw[1], c2 = cntw[2], c3 = cntw[3];
+                    const int m0 = kMapsPerWin * wi;
+                    const uint32_t seqbase = wseq + (m0 > 0 ? c0 : 0u) + (m0 > 1 ? c1 : 0u) + (m0 > 2 ? c2 : 0u);
+                    wseq += c0 + c1 + c2 + c3;
+                    if (lane == 0) mbar_arrive(BAR(CNT_READY + slot));
+                    TLAP(tw_bar2);
+                    if (DBG) tw_n += mr[0].nwin;
+                    if (trole >= 0 && lane == 0) { TRACE(trole, kcount, 1, c0); if (DBG && P.dbg && blockIdx.x == 0 && kcount < (uint32_t)kTraceJobs) P.dbg[(size_t)gridDim.x * kDbgStride + trole * 1024 + kcount * 8 + 7] = mr[0].nwin; }
+                    uint32_t seq0 = seqbase;
+#pragma unroll
+                    for (int mm = 0; mm < kMapsPerWin; ++mm) {
+                        const MapRows& r = mr[mm];
+                        const int nwin = r.nwin;
+                        if (mm > 0) seq0 += (uint32_t)mr[mm - 1].nwin;
+                        const CUtensorMap* tm = &P.mlp.tmap[kMapsPerWin * wi + mm];
                         // Ring slots must be acquired in sequence order: a parity wait is only unambiguous while the waiter is at most
-                        // one phase ahead of the barrier, so window s may wait for its slot only after window s - kRing holds it.  The four
-                        // window warps therefore take turns (enumeration above runs in parallel; issuing is ~100 cycles per window).
-                        volatile uint32_t* turn = reinterpret_cast<volatile uint32_t*>(sgen + SM_CNT + 36);
+                        // one phase ahead of the barrier, so window s may wait for its slot only after window s - kRing holds it.  The
+                        // window warps therefore take turns for the acquisition (a few instructions per window); the rest runs in parallel.
                         if (nwin > 0) {
                             if (lane == 0) {
                                 uint32_t spins = 0;
                                 while (*turn != seq0) {
-                                    __nanosleep(40);
-                                    if (++spins > 0x1000000u) mbar_timeout(P.trap, 4, (uint32_t)seq0, *turn);
+                                    if (++spins > 0x2000000u) mbar_timeout(P.trap, 4, (uint32_t)seq0, *turn);
                                 }
                             }
                             __syncwarp();
                         }
                         TLAP(tw_turn);
-                        if (trole >= 0 && lane == 0) { TRACE(trole, kcount, 4, 0); TRACE(trole, kcount, 6, nwin); if (DBG && blockIdx.x == 0 && kcount < (uint32_t)kTraceJobs) P.dbg[(size_t)gridDim.x * kDbgStride + trole * 1024 + kcount * 8 + 7] = nwin; }
-                        for (int i = 0; i < nwin; ++i) {
-                            const unsigned qa = __ballot_sync(0xffffffffu, ca == i), qb = __ballot_sync(0xffffffffu, cb == i);
-                            const int key = qa ? __shfl_sync(0xffffffffu, ka, __ffs(qa) - 1) : __shfl_sync(0xffffffffu, kb, __ffs(qb) - 1);
-                            const int ox = xm + 3 * (key & 0xffff), oy = ym + 3 * (key >> 16);
-                            const uint32_t seq = seq0 + (uint32_t)i, rs = seq % kRing, rpar = (seq / kRing) & 1u;
-                            if (lane == 0) {
-                                mbar_wait<kProdSleep>(BAR(WIN_EMPTY + rs), rpar ^ 1u, P.trap, 3);
-                                TLAP(tw_empty);
-                                mbar_expect_tx(BAR(WIN_FULL + rs), WIN_BYTES);
-                                tma_load_window(sbase + SM_WIN + rs * WIN_BYTES, tm, ox, oy, v * 4, BAR(WIN_FULL + rs));
-                            }
-                            __syncwarp();
-                            const uint32_t wt = sbase + SM_WT + rs * WT_BYTES;
+                        // Everything that does not need the ring is done BEFORE the slots are requested (the warp is usually blocked there):
+                        // each row's 16 window-slot weights as four 64-bit words (one per window row: the quad's top pair sits in window
+                        // row by at columns bx, bx+1, the bottom pair in row by+1), relative to the origin of the row's own box.
+                        unsigned long long wa[4], wb[4];
+                        {
+                            const int oxa = r.xm + 3 * (r.ka & 0xffff), oya = r.ym + 3 * (r.ka >> 16);
+                            const int oxb = r.xm + 3 * (r.kb & 0xffff), oyb = r.ym + 3 * (r.kb >> 16);
+                            const bool va = r.ca >= 0, vb = r.cb >= 0;
+                            const int bxa = va ? (int)r.ra.x - oxa : 0, bya = va ? (int)r.ra.y - oya : 0;
+                            const int bxb = vb ? (int)r.rb.x - oxb : 0, byb = vb ? (int)r.rb.y - oyb : 0;
+                            const unsigned long long ta = ((unsigned long long)r.ra.z) << (16 * bxa), ba_ = ((unsigned long long)r.ra.w) << (16 * bxa);
+                            const unsigned long long tb = ((unsigned long long)r.rb.z) << (16 * bxb), bb_ = ((unsigned long long)r.rb.w) << (16 * bxb);
 #pragma unroll
-                            for (int rr = 0; rr < 2; ++rr) {
-                                const int r = lane + 32 * rr;
-                                const bool mine = (rr ? cb : ca) == i;
-                                const uint4 ri = rr ? rb : ra;
-                                // the 16 texel slots of the window, one 64-bit word per window row: the quad's top pair sits in window
-                                // row by at columns bx, bx+1, the bottom pair in row by+1
-                                const int bx = mine ? (int)ri.x - ox : 0, by = mine ? (int)ri.y - oy : 0;
-                                const unsigned long long top = ((unsigned long long)ri.z) << (16 * bx), bot = ((unsigned long long)ri.w) << (16 * bx);
-                                unsigned long long qw[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) qw[j] = !mine ? 0ull : (j == by) ? top : (j == by + 1) ? bot : 0ull;
-                                const uint32_t dst = wt + (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
-                                sts128(dst, make_uint4((uint32_t)qw[0], (uint32_t)(qw[0] >> 32), (uint32_t)qw[1], (uint32_t)(qw[1] >> 32)));
-                                sts128(dst + 128u, make_uint4((uint32_t)qw[2], (uint32_t)(qw[2] >> 32), (uint32_t)qw[3], (uint32_t)(qw[3] >> 32)));
-                            }
-                            fence_proxy_async();                   // the tensor core (async proxy) reads the weight tile
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(BAR(WIN_FULL + rs));
-                            // the slot of window seq is held: the next window (this warp's or the next warp's) may acquire its own
-                            if (lane == 0) *turn = seq + 1u;
-                            TLAP(tw_body);
-                            if (DBG && m == 0 && i == nwin - 1 && lane == 0) {      // DBG only: TMA latency of the job's last latent window
-                                mbar_wait(BAR(WIN_FULL + rs), rpar, P.trap, 5);
-                                TLAP(tw_lat);
+                            for (int j = 0; j < 4; ++j) {
+                                wa[j] = !va ? 0ull : (j == bya) ? ta : (j == bya + 1) ? ba_ : 0ull;
+                                wb[j] = !vb ? 0ull : (j == byb) ? tb : (j == byb + 1) ? bb_ : 0ull;
                             }
                         }
+                        // Batches of at most kRing / 2 windows: (1) lane k acquires the ring slot of window k and starts its TMA load (the
+                        // turn passes on as soon as this map's last slot is held), (2) every lane stores its two rows into the batch's
+                        // tiles (zeros where the row belongs to another box), (3) ONE proxy fence, (4) lane k signals window k.
+                        for (int done = 0; done < nwin;) {
+                            const int nb = min(nwin - done, kRing / 2);
+                            int my_ox = 0, my_oy = 0;                       // lane k: origin of window done + k
+                            for (int k = 0; k < nb; ++k) {
+                                const int i = done + k;
+                                const unsigned qa = __ballot_sync(0xffffffffu, r.ca == i), qb = __ballot_sync(0xffffffffu, r.cb == i);
+                                const int key = qa ? __shfl_sync(0xffffffffu, r.ka, __ffs(qa) - 1) : __shfl_sync(0xffffffffu, r.kb, __ffs(qb) - 1);
+                                if (lane == k) { my_ox = r.xm + 3 * (key & 0xffff); my_oy = r.ym + 3 * (key >> 16); }
+                            }
+                            if (lane < nb) {
+                                const uint32_t seq = seq0 + (uint32_t)(done + lane), rs = seq % kRing, rpar = (seq / kRing) & 1u;
+                                mbar_wait<kProdSleep>(BAR(WIN_EMPTY + rs), rpar ^ 1u, P.trap, 3);
+                                mbar_expect_tx(BAR(WIN_FULL + rs), WIN_BYTES);
+                                tma_load_window(sbase + SM_WIN + rs * WIN_BYTES, tm, my_ox, my_oy, v * 4, BAR(WIN_FULL + rs));
+                            }
+                            __syncwarp();
+                            if (lane == 0 && done + nb == nwin) *turn = seq0 + (uint32_t)nwin;
+                            TLAP(tw_empty);
+                            const uint32_t rowoff_a = (uint32_t)(lane >> 3) * 256u + (uint32_t)(lane & 7) * 16u, rowoff_b = rowoff_a + 1024u;
+                            for (int k = 0; k < nb; ++k) {
+                                const int i = done + k;
+                                const uint32_t wt = sbase + SM_WT + ((seq0 + (uint32_t)i) % kRing) * WT_BYTES;
+                                const bool ma = r.ca == i, mb = r.cb == i;
+                                sts128(wt + rowoff_a, ma ? make_uint4((uint32_t)wa[0], (uint32_t)(wa[0] >> 32), (uint32_t)wa[1], (uint32_t)(wa[1] >> 32)) : make_uint4(0u, 0u, 0u, 0u));
+                                sts128(wt + rowoff_a + 128u, ma ? make_uint4((uint32_t)wa[2], (uint32_t)(wa[2] >> 32), (uint32_t)wa[3], (uint32_t)(wa[3] >> 32)) : make_uint4(0u, 0u, 0u, 0u));
+                                sts128(wt + rowoff_b, mb ? make_uint4((uint32_t)wb[0], (uint32_t)(wb[0] >> 32), (uint32_t)wb[1], (uint32_t)(wb[1] >> 32)) : make_uint4(0u, 0u, 0u, 0u));
+                                sts128(wt + rowoff_b + 128u, mb ? make_uint4((uint32_t)wb[2], (uint32_t)(wb[2] >> 32), (uint32_t)wb[3], (uint32_t)(wb[3] >> 32)) : make_uint4(0u, 0u, 0u, 0u));
+                            }
+                            fence_proxy_async();                   // the tensor core (async proxy) reads the weight tiles
+                            __syncwarp();
+                            if (lane < nb) mbar_arrive(BAR(WIN_FULL + (seq0 + (uint32_t)(done + lane)) % kRing));
+                            TLAP(tw_body);
+                            done += nb;
+                        }
                     }
-                    TLAP(tp_gather);
-                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 5, 0);
+                    if (trole >= 0 && lane == 0) TRACE(trole, kcount, 3, 0);
                 }
             }
         }
-        if (DBG && P.dbg && ptid == 0) {
+        if (DBG && P.dbg && wi == 0 && lane == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
-            d[0] = tp_pts; d[1] = tp_encwait; d[2] = tp_geom; d[3] = tp_bar; d[4] = tp_gwait; d[5] = tp_gather;
-            d[24] = tw_enum; d[25] = tw_bar2; d[26] = tw_turn; d[27] = tw_empty; d[28] = tw_body; d[29] = tw_n; d[30] = tw_lat; d[31] = tw_lds; d[32] = tw_red; d[33] = tw_loop;
+            d[0] = tw_wait; d[24] = tw_enum; d[25] = tw_bar2; d[26] = tw_turn; d[27] = tw_empty; d[28] = tw_body; d[29] = tw_n;
         }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // =====================================================================================
         // MMA ISSUE (one thread)
         // =====================================================================================
@@ -1046,7 +1101,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                 }
                 __syncwarp();
             };
-            for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            uint32_t tcount = 0;
+            for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x, ++tcount) {
                 for (int v = 0; v < nv; ++v) {
                     for (int h = 0; h < 2; ++h, ++kcount) {
                         const uint32_t slot = kcount & 1, use = (kcount >> 1) & 1;
@@ -1077,15 +1133,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                         auto win_a = [&](uint32_t rs, int half3) { return desc_mn_sw128(sbase + SM_WIN + rs * WIN_BYTES + half3 * 4096, 2048, 1024); };
                         auto win_b = [&](uint32_t rs) { return desc_nosw(sbase + SM_WT + rs * WT_BYTES, 128, 256); };
                         if (nwin <= (uint32_t)kRing) {
-                            for (uint32_t i = 0; i < nwin; ++i) {
-                                const uint32_t seq = whead + i, rs = seq % kRing;
-                                mbar_wait(BAR(WIN_FULL + rs), (seq / kRing) & 1u, P.trap, 13);
-                                tc_fence_after();
-                                if (elect_one()) mma_ss(dD, win_a(rs, 0), win_b(rs), id_win, 1);
-                                __syncwarp();
+                            if ((uint32_t)lane < nwin) {                     // lane i waits for window i: the waits overlap
+                                const uint32_t seq = whead + (uint32_t)lane;
+                                mbar_wait(BAR(WIN_FULL + seq % kRing), (seq / kRing) & 1u, P.trap, 13);
                             }
+                            __syncwarp();
+                            tc_fence_after();
                             TLAP(tm_gwait);
                             if (elect_one()) {
+                                for (uint32_t i = 0; i < nwin; ++i) {
+                                    const uint32_t rs = (whead + i) % kRing;
+                                    mma_ss(dD, win_a(rs, 0), win_b(rs), id_win, 1);
+                                }
                                 tc_commit(BAR(ACC_READY));
                                 tc_commit(BAR(ACC_READY + 1));
 #pragma unroll
@@ -1149,6 +1208,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                     // the previous tile's colour head (drained during this tile's first job) has left the head accumulator
                     if (v == 0 && pend) { wait_bar(HEAD_DONE, ph_done, 17); pend = false; }
                     // head: Dh (+)= H3 . (Whead_h)^T      (128 points on lanes, accumulates the view mean)
+                    if (v == nv - 1) { mbar_wait(BAR(DIR_READY), tcount & 1u, P.trap, 19); tc_fence_after(); }     // the tile's direction encodings are staged
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
@@ -1173,11 +1233,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
         }
     } else {
         // =====================================================================================
-        // EPILOGUE (4 warps).  Trunk: thread = neuron (TMEM lane).  Head: thread = point.
+        // EPILOGUE (2 sets of 4 warps; a warp reads the TMEM lane quarter warp % 4).  Set A (warps 0-3) serves the 32-point block 0
+        // of every half-job and the colour head, set B (warps 4-7) block 1: the two blocks' epilogues run concurrently, so the
+        // tensor pipe works on one block's next layer while the other block is being converted.
+        // Trunk: thread = neuron (TMEM lane).  Head: thread = point.
         // =====================================================================================
-        const int c = warp * 32 + lane;                 // neuron (trunk) / point row (head)
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ph_acc = 0, ph_head = 0;     // bit b = parity of ACC_READY[b]
+        const int eset = warp >> 2, wq = warp & 3;
+        const int c = wq * 32 + lane;                   // neuron (trunk) / point row (head)
+        const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
+        uint32_t ph_acc = 0, ph_head = 0;     // parity of ACC_READY[eset]
         long long te_accwait = 0, te_gwait = 0, te_work = 0, te_head = 0;
         long long te_g_j[8] = {0, 0, 0, 0, 0, 0, 0, 0}, te_acc_l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         TSTART();
@@ -1200,36 +1264,48 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
             if (stage == 0) {
                 mbar_wait(BAR(HEAD_READY), ph_head, P.trap, 26); ph_head ^= 1;
                 tc_fence_after();
-                uint32_t r[80];
+                {
+                    uint32_t rs[8];
+                    tmem_ld8(lane_base + TM_DH + 64, rs);
+                    tc_wait_ld();
+                    const float raw = __uint_as_float(rs[0]) + lds_f32(sBias + 4 * 644);
+                    const float xs = raw - 1.0f;                                       // model.py:392-393
+                    if (valid) P.sigma_out[gp] = xs > 20.f ? xs : log1pf(expf(xs));
+                }
+                // 16 accumulator columns at a time: the colour head is off the critical path, registers are not
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[16];
+                    tmem_ld16(lane_base + TM_DH + 16 * j, r);
+                    tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 5; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
-                tc_wait_ld();
-                const float raw = __uint_as_float(r[64]) + lds_f32(sBias + 4 * 644);
-                const float xs = raw - 1.0f;                                       // model.py:392-393
-                if (valid) P.sigma_out[gp] = xs > 20.f ? xs : log1pf(expf(xs));
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ch = 2 * j + c2;
+                        float y[8];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (512 + ch * 8 + i)), 0.f);
-                    sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
-                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                        for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[c2 * 8 + i]) + lds_f32(sBias + 4 * (512 + ch * 8 + i)), 0.f);
+                        sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
+                               make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                    }
                 }
                 tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
             } else if (stage == 1) {
                 mbar_wait(BAR(CH_READY), ph_ch, P.trap, 27); ph_ch ^= 1;
                 tc_fence_after();
-                uint32_t r[64];
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[16];
+                    tmem_ld16(lane_base + TM_DH + 16 * j, r);
+                    tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tmem_ld16(lane_base + TM_DH + 16 * j, r + 16 * j);
-                tc_wait_ld();
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ch = 2 * j + c2;
+                        float y[8];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[ch * 8 + i]) + lds_f32(sBias + 4 * (576 + ch * 8 + i)), 0.f);
-                    sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
-                           make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                        for (int i = 0; i < 8; ++i) y[i] = fmaxf(__uint_as_float(r[c2 * 8 + i]) + lds_f32(sBias + 4 * (576 + ch * 8 + i)), 0.f);
+                        sts128(sQ + c * 128 + ((ch ^ (c & 7)) << 4),
+                               make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7])));
+                    }
                 }
                 tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(BAR(Q_READY), lane);
             } else {
@@ -1260,12 +1336,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                         // biases arrive through the bias MMA and the gathered features through the transpose-accumulate MMA, so every
                         // layer is: TMEM load -> fp16 pack -> packed ReLU -> 4 x 16-byte stores of this neuron's K row
                         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll 1
-                        for (int bb = 0; bb < 2; ++bb) {
+                        {
+                            const int bb = eset;
                             unsigned char* hp = sgen + (sHh - sbase) + hbase;
                             uint32_t r[32];
                             TLAP(te_work);
-                            mbar_wait(BAR(ACC_READY + bb), (ph_acc >> bb) & 1u, P.trap, 20 + l); ph_acc ^= 1u << bb;
+                            mbar_wait(BAR(ACC_READY + bb), ph_acc, P.trap, 20 + l); ph_acc ^= 1u;
                             if (DBG) { long long t1 = clock64(); te_acc_l[l * 2 + bb] += t1 - _t0; }
                             TLAP(te_accwait);
                             tc_fence_after();
@@ -1286,13 +1362,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                             fence_proxy_async();
                             mbar_arrive_warp(BAR(H_READY + bb), lane);
                         }
-                        if (pend && v == 0 && h == 0 && l < 3) head_stage(l, pg, pq);
+                        if (eset == 0 && pend && v == 0 && h == 0 && l < 3) head_stage(l, pg, pq);
                     }
                 }
             }
             pend = true; pg = g; pq = q;       // colour head of this tile: interleaved with the next tile's first job (or drained below)
         }
-        if (pend) { head_stage(0, pg, pq); head_stage(1, pg, pq); head_stage(2, pg, pq); }
+        if (eset == 0 && pend) { head_stage(0, pg, pq); head_stage(1, pg, pq); head_stage(2, pg, pq); }
         if (DBG && P.dbg && threadIdx.x == 0) {
             long long* d = P.dbg + (size_t)blockIdx.x * kDbgStride;
             d[9] = te_accwait; d[10] = te_gwait; d[11] = te_work; d[12] = te_head;
@@ -1302,7 +1378,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------

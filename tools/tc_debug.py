@@ -21,28 +21,42 @@ with torch.no_grad():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.render_rays_test(rays, chunk=1024); e1.record(); torch.cuda.synchronize()
+    mlp = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    if mlp != 3:      # make another branch the LAST launch: re-evaluate its field on the frame's own t-values
+        lib.neo_tc_debug(None)
+        net.forward(rays, False, False, None, None, out_depth=True, chunk=1024, debug=True)
+        dbg = net.last_debug
+        tk = ("fg_t", "bg_s")[mlp & 1]
+        tv = dbg[tk][mlp >> 1]
+        from neo360_b200 import ops
+        far = ops.intersect_sphere(rays["rays_o"], rays["rays_d"])
+        buf.zero_()
+        lib.neo_tc_debug(buf.data_ptr())
+        net.field_eval(rays, far, tv, mlp, chunk=1024)
+        torch.cuda.synchronize()
     lib.neo_tc_debug(None)
 ms = e0.elapsed_time(e1)
 tr = buf[148 * 64:].view(5, 128, 8).cpu()
 b = buf[:148 * 64].view(148, 64).double().cpu()
-names = ["P pts", "P wait ENC_FREE", "P geometry", "P bar", "P (unused)", "P windows", "M wait ENC_READY", "M wait H_READY", "M issue",
+names = ["W wait INFO_READY", "G wait slots", "G geometry", "-", "-", "-", "M wait ENC_READY", "M wait H_READY", "M issue",
          "E wait ACC", "E wait G", "E work", "E head", "M wait windows"]
 # counters are overwritten by each of the 4 field launches: they hold the LAST launch (bg fine, N=193)
-tiles = ((n + 31) // 32) * ((193 + 3) // 4)
+NN = 193 if (int(sys.argv[4]) if len(sys.argv) > 4 else 3) >= 2 else 129
+tiles = ((n + 31) // 32) * ((NN + 3) // 4)
 halfjobs_per_cta = tiles * 6 / 148
 print(f"{n} rays, frame step {ms:.1f} ms; last launch: {tiles} tiles, {halfjobs_per_cta:.0f} half-jobs per CTA")
 for i, nm in enumerate(names):
     print(f"  {nm:18s} {b[:, i].mean() / halfjobs_per_cta:9.0f} cycles / half-job   (total {b[:, i].mean() / 1e6:8.2f} Mcyc)")
 
 jobs_per_bin = halfjobs_per_cta / 6
-for i, nm in enumerate(["W enumerate", "W bar.sync 2", "W turn", "W wait EMPTY", "W issue+weights", "W latent windows (count)", "W TMA latency (last latent window)", "W  lds rowinfo", "W  fence.proxy.async", "W  arrive ENC_READY"]):
+for i, nm in enumerate(["W enumerate", "W bar.sync 2", "W turn", "W acquire + TMA", "W weights + fence", "W latent windows (count)"]):
     print(f"  {nm:36s} {b[:, 24 + i].mean() / halfjobs_per_cta:9.1f} per half-job")
 print("  E wait ACC by layer,block   " + " ".join(f"{b[:, 40 + i].mean() / halfjobs_per_cta:6.0f}" for i in range(8)))
 
 # event trace of CTA 0 (last launch), cycles relative to the MMA warp's first stamp
 t0 = int(tr[3, 0, 0])
-print("job | P0: encfree geom bar1 bar2 turn done nwin | P1: encfree geom bar1 | P6: bar2 turn done nwin | MMA: enc cnt win l3 end nwin")
+print("job | G0: start done | W0 (latent, xz): info cnt - done nwin | W1 (xy, yz): info cnt - done nwin | MMA: enc cnt win l3 end nwin")
 for j in range(int(sys.argv[2]) if len(sys.argv) > 2 else 8, int(sys.argv[3]) if len(sys.argv) > 3 else 40):
     r = lambda role, k: int(tr[role, j, k]) - t0 if int(tr[role, j, k]) else -1
-    print(f"{j:3d} | {r(0,0):7d} {r(0,1):7d} {r(0,2):7d} {r(0,3):7d} {r(0,4):7d} {r(0,5):7d} {int(tr[0,j,7]):2d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} | "
-          f"{r(2,3):7d} {r(2,4):7d} {r(2,5):7d} {int(tr[2,j,7]):2d} | {r(3,0):7d} {r(3,1):7d} {r(3,2):7d} {r(3,3):7d} {r(3,4):7d} {int(tr[3,j,7]):2d}")
+    print(f"{j:3d} | {r(0,0):7d} {r(0,1):7d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} {r(1,3):7d} {int(tr[1,j,7]):2d} | "
+          f"{r(2,0):7d} {r(2,1):7d} {r(2,2):7d} {r(2,3):7d} {int(tr[2,j,7]):2d} | {r(3,0):7d} {r(3,1):7d} {r(3,2):7d} {r(3,3):7d} {r(3,4):7d} {int(tr[3,j,7]):2d}")
