@@ -174,6 +174,25 @@ int neo_volumetric_rendering(const float* rgb, const float* sigma, const float* 
 int neo_index_grid(const NeoScene* scene, const float* pts, int M, float* out, void* stream);
 /* model.py:239-264 (get_local_feats): pts (M,3) world -> (nv*M,512). */
 int neo_index_local(const NeoScene* scene, const float* pts, int M, float* out, void* stream);
+/* Output side (models/interface.py:53-61, LitModel.psnr_each): *out_sum (device double) = sum_i (clip(pred_i,0,1) - clip(gt_i,0,1))^2 over n
+ * floats; PSNR = -10 log10(out_sum / n). */
+int neo_clipped_sq_err(const float* pred, const float* gt, long long n, double* out_sum, void* stream);
+
+/* ---- backward of the hand-written stages (training: models/neo360/model.py:697-820 differentiates through this path) ----
+ * The field's backward is split: the lookups' scatter and the compositing backward are the entry points below; the dense layers of
+ * NeRFPPMLP are differentiated by the host framework (plain library GEMMs) in neo360_b200/training.py.  Sample positions carry no
+ * gradient (the reference detaches them, helper.py:225). */
+/* d(volumetric_rendering)/d(rgb, sigma): upstream gradients of comp_rgb (n,3), acc (n), weights (n,N), bg_lambda (n), depth (n) -- any
+ * may be NULL -- -> d_rgb (n,N,3), d_sigma (n,N).  Same rgb / sigma / t / rays_d / far as the forward call. */
+int neo_volumetric_rendering_bwd(const float* rgb, const float* sigma, const float* t_vals, const float* rays_d, const float* far,
+                                 int n_rays, int N, int white_bkgd, int in_sphere, const float* g_comp_rgb, const float* g_acc,
+                                 const float* g_weights, const float* g_bg_lambda, const float* g_depth, float* d_rgb, float* d_sigma,
+                                 void* stream);
+/* d(index_grid)/d(planes): g_out (nv*M,128) -> ACCUMULATES into channel-last gradient maps (nv, plane_h, plane_w, 128) x3 (zeroed by the caller). */
+int neo_index_grid_bwd(const NeoScene* scene, const float* pts, int M, const float* g_out, float* g_planes_xz, float* g_planes_xy,
+                       float* g_planes_yz, void* stream);
+/* d(get_local_feats)/d(latent): g_out (nv*M,512) -> ACCUMULATES into the channel-last gradient map (nv, lat_h, lat_w, 512). */
+int neo_index_local_bwd(const NeoScene* scene, const float* pts, int M, const float* g_out, float* g_latent, void* stream);
 /* `predict` (model.py:343-407) for one branch of one level: t/s (n,N) -> rgb (n,N,3), sigma (n,N).
  * mlp_index in 0..3 = {fg_coarse,bg_coarse,fg_fine,bg_fine}; is_bg selects the NeRF++ background parametrisation. */
 int neo_field_eval(const NeoScene* scene, const NeoRays* rays, const float* far, const float* t_vals, int N,

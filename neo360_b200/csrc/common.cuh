@@ -210,9 +210,13 @@ int launch_resample(const float* o, const float* d, const float* far, const floa
 int launch_composite(const float* rgb, const float* sigma, const float* t, const float* d, const float* far, int n,
                      int N, int white, int in_sphere, float* comp, float* acc, float* w, float* lam, float* depth,
                      cudaStream_t s);
+int launch_composite_bwd(const float* rgb, const float* sigma, const float* t, const float* d, const float* far, int n, int N, int white,
+                         int in_sphere, const float* g_comp, const float* g_acc, const float* g_w, const float* g_lam, const float* g_depth,
+                         float* d_rgb, float* d_sigma, cudaStream_t s);
 int launch_combine(int n, int N, const float* fg_c, const float* bg_c, const float* lam, const float* fg_depth,
                    const float* bg_depth, const float* fg_t, const float* bg_s, float* comp, float* depth,
                    float* fg_sdist, float* bg_sdist, cudaStream_t s);
+int launch_clipped_sq_err(const float* a, const float* b, long long n, double* out, cudaStream_t s);
 int launch_get_rays(int H, int W, float focal, const float* c2w, float* o, float* vd, float* rd, float* radii,
                     cudaStream_t s);
 // field_fp32.cu
@@ -220,6 +224,8 @@ int launch_field_fp32(const NeoScene* sc, const NeoRays* rays, const float* far,
                       float* rgb, float* sigma, cudaStream_t s);
 int launch_index_grid(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s);
 int launch_index_local(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s);
+int launch_index_bwd(const NeoScene* sc, const float* pts, int M, int local, const float* g_out, float* g_lat, float* g_xz, float* g_xy,
+                     float* g_yz, cudaStream_t s);
 // field_tc.cu
 int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s);
 void tc_scene_free(NeoScene* sc);

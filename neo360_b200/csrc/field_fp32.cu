@@ -332,6 +332,58 @@ __global__ void index_kernel(SceneDev sc, const float* __restrict__ pts, int M, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward of the stage-level lookups: scatter-add of the row gradients into channel-last gradient maps
+// (nv, H, W, C): d map[v][tap texel][:] += w_tap * d out[row][:].  A row's channels are contiguous in both tensors, so the
+// atomics of one warp are 16-byte vector reductions on consecutive addresses (red.global.add.v4.f32).
+// ------------------------------------------------------------------------------------------------
+__global__ void index_bwd_kernel(SceneDev sc, const float* __restrict__ pts, int M, int local, const float* __restrict__ g_out,
+                                 float* __restrict__ g_lat, float* __restrict__ g_xz, float* __restrict__ g_xy, float* __restrict__ g_yz) {
+    const int C = local ? kLocalCh : kWorldCh;
+    const long long row = blockIdx.x;           // v*M + m
+    const int v = (int)(row / M), m = (int)(row % M);
+    float c[3];
+    to_camera(sc.views[v], pts + 3 * (size_t)m, c);
+    const float4* g = reinterpret_cast<const float4*>(g_out + row * C);
+    if (local) {
+        float gx, gy;
+        Taps t;
+        local_grid_coords(sc, c, gx, gy);
+        bilinear_taps(gx, gy, sc.lat_w, sc.lat_h, t);
+        float* base = g_lat + (size_t)v * sc.lat_h * sc.lat_w * kLocalCh;
+        for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
+            const float4 gv = g[q];
+            for (int tp = 0; tp < 4; ++tp) {
+                const float w = t.w[tp];
+                if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * kLocalCh) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
+            }
+        }
+    } else {
+        const float ga[3] = {c[0], c[0], c[1]}, gb[3] = {c[2], c[1], c[2]};
+        float* maps[3] = {g_xz, g_xy, g_yz};
+        for (int pi = 0; pi < 3; ++pi) {
+            Taps t;
+            bilinear_taps(ga[pi], gb[pi], sc.plane_w, sc.plane_h, t);
+            float* base = maps[pi] + (size_t)v * sc.plane_h * sc.plane_w * kWorldCh;
+            for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
+                const float4 gv = g[q];
+                for (int tp = 0; tp < 4; ++tp) {
+                    const float w = t.w[tp];
+                    if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * kWorldCh) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
+                }
+            }
+        }
+    }
+}
+
+int launch_index_bwd(const NeoScene* sc, const float* pts, int M, int local, const float* g_out, float* g_lat, float* g_xz, float* g_xy,
+                     float* g_yz, cudaStream_t s) {
+    index_bwd_kernel<<<(unsigned)((long long)sc->dev.nv * M), local ? 128 : 32, 0, s>>>(sc->dev, pts, M, local, g_out, g_lat, g_xz, g_xy, g_yz);
+    NEO_LAUNCH_CHECK("index_bwd_kernel");
+    return NEO_OK;
+}
+
 int launch_index_grid(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s) {
     index_kernel<<<(unsigned)((long long)sc->dev.nv * M), 128, 0, s>>>(sc->dev, pts, M, 0, out);
     NEO_LAUNCH_CHECK("index_kernel(grid)");

@@ -127,7 +127,7 @@ constexpr int kProdSleep = NEO_PROD_SLEEP_NS;
 // suspend-time hint of mbarrier.try_wait (ns): the hardware parks a waiting thread for up to this long between checks of the phase;
 // with a long hint a waiter that has been parked for a while is woken late (measured: ~2 us after the phase flipped)
 #ifndef NEO_TRYWAIT_HINT_NS
-#define NEO_TRYWAIT_HINT_NS 64
+#define NEO_TRYWAIT_HINT_NS 2000
 #endif
 #ifndef NEO_SPIN_POLLS
 #define NEO_SPIN_POLLS 16

@@ -189,6 +189,25 @@ extern "C" int neo_volumetric_rendering(const float* rgb, const float* sigma, co
     if (n <= 0 || N < 1) { set_error("neo_volumetric_rendering: bad sizes"); return NEO_ERR_INVALID; }
     return launch_composite(rgb, sigma, t, d, far, n, N, white, in_sphere, comp, acc, w, lam, depth, (cudaStream_t)stream);
 }
+extern "C" int neo_clipped_sq_err(const float* pred, const float* gt, long long n, double* out_sum, void* stream) {
+    if (n <= 0 || !pred || !gt || !out_sum) { set_error("neo_clipped_sq_err: bad arguments"); return NEO_ERR_INVALID; }
+    return launch_clipped_sq_err(pred, gt, n, out_sum, (cudaStream_t)stream);
+}
+extern "C" int neo_volumetric_rendering_bwd(const float* rgb, const float* sigma, const float* t, const float* d, const float* far, int n, int N,
+                                            int white, int in_sphere, const float* g_comp, const float* g_acc, const float* g_w,
+                                            const float* g_lam, const float* g_depth, float* d_rgb, float* d_sigma, void* stream) {
+    if (n <= 0 || N < 1 || !rgb || !sigma || !t || !d_rgb || !d_sigma) { set_error("neo_volumetric_rendering_bwd: bad arguments"); return NEO_ERR_INVALID; }
+    if (in_sphere != 0 && in_sphere != 1) { set_error("neo_volumetric_rendering_bwd: in_sphere must be 0 or 1"); return NEO_ERR_UNSUPPORTED; }
+    return launch_composite_bwd(rgb, sigma, t, d, far, n, N, white, in_sphere, g_comp, g_acc, g_w, g_lam, g_depth, d_rgb, d_sigma, (cudaStream_t)stream);
+}
+extern "C" int neo_index_grid_bwd(const NeoScene* sc, const float* pts, int M, const float* g_out, float* g_xz, float* g_xy, float* g_yz, void* stream) {
+    if (!sc || M <= 0 || !pts || !g_out || !g_xz || !g_xy || !g_yz) { set_error("neo_index_grid_bwd: bad arguments"); return NEO_ERR_INVALID; }
+    return launch_index_bwd(sc, pts, M, 0, g_out, nullptr, g_xz, g_xy, g_yz, (cudaStream_t)stream);
+}
+extern "C" int neo_index_local_bwd(const NeoScene* sc, const float* pts, int M, const float* g_out, float* g_latent, void* stream) {
+    if (!sc || M <= 0 || !pts || !g_out || !g_latent) { set_error("neo_index_local_bwd: bad arguments"); return NEO_ERR_INVALID; }
+    return launch_index_bwd(sc, pts, M, 1, g_out, g_latent, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
 extern "C" int neo_index_grid(const NeoScene* sc, const float* pts, int M, float* out, void* stream) {
     if (!sc || M <= 0 || !sc->dev.planes_cl[0]) { set_error("neo_index_grid: needs a scene prepared with NEO_PREC_FP32"); return NEO_ERR_INVALID; }
     return launch_index_grid(sc, pts, M, out, (cudaStream_t)stream);

@@ -369,6 +369,71 @@ int launch_composite(const float* rgb, const float* sigma, const float* t, const
     return NEO_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward of a12 (volumetric_rendering, helper.py:128-171) w.r.t. the per-sample rgb and sigma (t is detached in the reference:
+// sample positions carry no gradient, helper.py:225).  One thread per ray, two sequential passes over its N samples:
+//   forward  : T_i = prod_{j<i} (1 - alpha_j + 1e-10)                       (kept in the d_sigma row as scratch)
+//   backward : G_i = g_comp.c_i + g_w_i + g_acc + g_depth t_i - white * sum(g_comp)        (dL/dw_i)
+//              S_i = sum_{j>i} G_j w_j + g_lam T_N                                          (everything downstream of factor a_i)
+//              dL/dalpha_i = G_i T_i - S_i / a_i ,   dL/dsigma_i = dL/dalpha_i * delta_i (1 - alpha_i) ,   dL/dc_i = w_i g_comp
+// ------------------------------------------------------------------------------------------------
+__global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma, const float* __restrict__ t,
+                                     const float* __restrict__ d, const float* __restrict__ far, int n, int N, int white, int in_sphere,
+                                     const float* __restrict__ g_comp, const float* __restrict__ g_acc, const float* __restrict__ g_w,
+                                     const float* __restrict__ g_lam, const float* __restrict__ g_depth,
+                                     float* __restrict__ d_rgb, float* __restrict__ d_sigma) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const float* tb = t + (long long)b * N;
+    const float* sb = sigma + (long long)b * N;
+    const float* cb = rgb + (long long)b * N * 3;
+    float* ds = d_sigma + (long long)b * N;
+    float* dc = d_rgb + (long long)b * N * 3;
+    float dn = 1.f, fr = 0.f;
+    if (in_sphere) {
+        const float* dd = d + 3 * b;
+        dn = __fsqrt_rn(dot3_(dd, dd));
+        fr = far[b];
+    }
+    auto dist_of = [&](int k) -> float {
+        if (in_sphere) return mul_(sub_((k + 1 < N) ? tb[k + 1] : fr, tb[k]), dn);
+        return (k + 1 < N) ? sub_(tb[k], tb[k + 1]) : 1e10f;
+    };
+    float T = 1.f;
+    for (int k = 0; k < N; ++k) {
+        ds[k] = T;
+        const float alpha = sub_(1.0f, expf(-mul_(sb[k], dist_of(k))));
+        T = mul_(T, add_(sub_(1.0f, alpha), 1e-10f));
+    }
+    const float gc[3] = {g_comp ? g_comp[b * 3] : 0.f, g_comp ? g_comp[b * 3 + 1] : 0.f, g_comp ? g_comp[b * 3 + 2] : 0.f};
+    const float ga = (g_acc ? g_acc[b] : 0.f) - (white ? (gc[0] + gc[1] + gc[2]) : 0.f);
+    const float gd = g_depth ? g_depth[b] : 0.f;
+    float S = (g_lam ? g_lam[b] : 0.f) * T;
+    for (int k = N - 1; k >= 0; --k) {
+        const float Tk = ds[k];
+        const float dist = dist_of(k);
+        const float e = expf(-mul_(sb[k], dist));
+        const float alpha = sub_(1.0f, e);
+        const float a = add_(sub_(1.0f, alpha), 1e-10f);
+        const float w = alpha * Tk;
+        const float G = gc[0] * cb[3 * k] + gc[1] * cb[3 * k + 1] + gc[2] * cb[3 * k + 2] + (g_w ? g_w[(long long)b * N + k] : 0.f) + ga + gd * tb[k];
+        const float dalpha = G * Tk - S / a;
+        ds[k] = dalpha * dist * e;            // d alpha / d sigma = delta exp(-sigma delta)
+        dc[3 * k] = w * gc[0]; dc[3 * k + 1] = w * gc[1]; dc[3 * k + 2] = w * gc[2];
+        S += G * w;
+    }
+}
+
+int launch_composite_bwd(const float* rgb, const float* sigma, const float* t, const float* d, const float* far, int n, int N, int white,
+                         int in_sphere, const float* g_comp, const float* g_acc, const float* g_w, const float* g_lam, const float* g_depth,
+                         float* d_rgb, float* d_sigma, cudaStream_t s) {
+    composite_bwd_kernel<<<(n + 127) / 128, 128, 0, s>>>(rgb, sigma, t, d, far, n, N, white, in_sphere, g_comp, g_acc, g_w, g_lam, g_depth,
+                                                         d_rgb, d_sigma);
+    NEO_LAUNCH_CHECK("composite_bwd_kernel");
+    return NEO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // a13  fg + bg_lambda * bg, sdist outputs   (model.py:521-527, 564-579)
 // ------------------------------------------------------------------------------------------------
@@ -411,6 +476,35 @@ int launch_combine(int n, int N, const float* fg_c, const float* bg_c, const flo
     combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n, N, fg_c, bg_c, lam, fg_depth, bg_depth, fg_t, bg_s,
                                                                  comp, depth, fg_sdist, bg_sdist);
     NEO_LAUNCH_CHECK("combine_kernel");
+    return NEO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// output side: sum of squared differences of two images after clipping to [0,1] -- the reduction under
+// LitModel.psnr_each (models/interface.py:53-61).  Grid-stride, warp + block reduction, one double atomicAdd per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void clipped_sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = fminf(fmaxf(a[i], 0.f), 1.f) - fminf(fmaxf(b[i], 0.f), 1.f);
+        acc += (double)(x * x);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+int launch_clipped_sq_err(const float* a, const float* b, long long n, double* out, cudaStream_t s) {
+    NEO_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    clipped_sq_err_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(a, b, n, out);
+    NEO_LAUNCH_CHECK("clipped_sq_err_kernel");
     return NEO_OK;
 }
 

@@ -201,9 +201,8 @@ class NeRF_TP(nn.Module):
     def forward(self, rays: Dict[str, torch.Tensor], randomized: bool, white_bkgd: bool, near=None, far=None,
                 out_depth: bool = False, chunk: Optional[int] = None, debug: bool = False) -> List[tuple]:
         """near/far are ignored exactly as the reference ignores them (quirk Q4, model.py:277-278)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("backward through the fused CUDA path is not built yet (SURVEY.md 8(f2)); "
-                                      "call under torch.no_grad() / .eval()")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(rays, randomized, white_bkgd, out_depth)
         lib = L.load()
         sc = self._ensure_scene(rays)
         o = rays["rays_o"].contiguous().float()
@@ -273,6 +272,30 @@ class NeRF_TP(nn.Module):
         if debug:
             self.last_debug = T
         return ret
+
+    def _forward_train(self, rays, randomized, white_bkgd, out_depth):
+        """Training mode (models/neo360/model.py:725-732): the same tuples, differentiable w.r.t. the MLP parameters and the encoder
+        outputs.  The feature maps come from the `rays` dict (`planes_xz|xy|yz`, `latent`), from `self.encoder` (run WITH autograd, so
+        its parameters train too) or from the last `set_scene`.  See neo360_b200/training.py for what is hand-written CUDA."""
+        from . import training
+        if all(k in rays for k in ("planes_xz", "planes_xy", "planes_yz", "latent")):
+            maps = [rays[k] for k in ("planes_xz", "planes_xy", "planes_yz", "latent")]
+            cams = [rays[k] for k in ("src_poses", "src_focal", "src_c")]
+            wh = (rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2]) if "src_imgs" in rays else self._scene_inputs[7]
+        elif self.encoder is not None and "src_imgs" in rays:
+            xz, xy, yz = self.encoder(rays["src_imgs"], rays["src_poses"], rays["src_focal"], rays["src_c"])
+            maps = [xz, xy, yz, self.encoder.spatial_encoder.latent]
+            cams = [rays[k] for k in ("src_poses", "src_focal", "src_c")]
+            wh = (rays["src_imgs"].shape[-1], rays["src_imgs"].shape[-2])
+        elif self._scene_inputs is not None:
+            a = self._scene_inputs
+            maps, cams, wh = list(a[:4]), list(a[4:7]), a[7]
+        else:
+            raise RuntimeError("no scene: call set_scene(...) or pass planes_*/latent in `rays`, or give an encoder")
+        self.set_scene(*maps, *cams, wh, precisions=["fp32"])          # the lookups read the scene's channel-last copies of THESE maps
+        r = dict(rays)
+        r["src_poses"] = cams[0]
+        return training.render_train(self, r, maps[:3], maps[3], randomized, white_bkgd, out_depth, uniforms=rays.get("_uniforms"))
 
     # ---- stage-level operators that need the scene (parity tests) ----
     def index_grid(self, samples: torch.Tensor) -> torch.Tensor:

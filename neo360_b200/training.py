@@ -1,0 +1,280 @@
+"""Differentiable (training) form of the NeO-360 hot path: `NeRF_TP.forward(..., out_depth=False)` under autograd.
+
+Reference: models/neo360/model.py:266-581 (train tuple 564-579), training_step 697-820, distortion loss 1246-1260, DDP run.py:154.
+
+What runs where
+  * hand-written CUDA through the C ABI: ray / sphere intersection, stratified + inverse-CDF sampling (no gradient: the reference
+    detaches sample positions, helper.py:225), the tri-plane and pixel-aligned lookups (forward `neo_index_grid|local`, backward
+    `neo_index_grid_bwd|local_bwd`: 16-byte vector reductions into channel-last gradient maps), alpha compositing (forward
+    `neo_volumetric_rendering`, backward `neo_volumetric_rendering_bwd`);
+  * host framework (autograd + plain library GEMMs): the dense layers of NeRFPPMLP, activations, positional encodings, losses and the
+    optimiser.  The tensor-core inference kernel (csrc/field_tc.cu) re-associates the network per scene (pre-projected maps), which
+    does not survive a weight update per step -- training keeps the reference formulation.
+  * NCCL: ONE all-reduce over the flat gradient slab of the four MLPs per step (`allreduce_flat`), as the reference's DDP does.
+There is no CPU fallback: every op raises on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Lookup(torch.autograd.Function):
+    """index_grid + get_local_feats (encoder_tp_fusion_conv.py:122-209, model.py:239-264) of world points (M,3):
+    -> world (NV*M,128), local (NV*M,512); gradients flow to the three tri-planes and the latent image."""
+
+    @staticmethod
+    def forward(ctx, pts, planes_xz, planes_xy, planes_yz, latent, net):
+        lib = L.load()
+        p = pts.detach().reshape(-1, 3).contiguous().float()
+        sc = net._scene
+        M, nv = p.shape[0], sc.nv
+        world = torch.empty(nv * M, 128, device=p.device)
+        local = torch.empty(nv * M, 512, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(lib.neo_index_grid(sc.handle, L.ptr(p), M, L.ptr(world), _stream()))
+            L.check(lib.neo_index_local(sc.handle, L.ptr(p), M, L.ptr(local), _stream()))
+        ctx.save_for_backward(p)
+        ctx.net, ctx.scene = net, sc
+        ctx.shapes = (planes_xz.shape, latent.shape)
+        return world, local
+
+    @staticmethod
+    def backward(ctx, g_world, g_local):
+        lib = L.load()
+        (p,) = ctx.saved_tensors
+        sc = ctx.scene
+        (nv, cw, hp, wp), (_, cl, hl, wl) = ctx.shapes
+        M = p.shape[0]
+        g_planes = [torch.zeros(nv, hp, wp, cw, device=p.device) for _ in range(3)]
+        g_lat = torch.zeros(nv, hl, wl, cl, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(lib.neo_index_grid_bwd(sc.handle, L.ptr(p), M, L.ptr(g_world.contiguous().float()), L.ptr(g_planes[0]), L.ptr(g_planes[1]),
+                                           L.ptr(g_planes[2]), _stream()))
+            L.check(lib.neo_index_local_bwd(sc.handle, L.ptr(p), M, L.ptr(g_local.contiguous().float()), L.ptr(g_lat), _stream()))
+        nchw = lambda t: t.permute(0, 3, 1, 2)
+        return None, nchw(g_planes[0]), nchw(g_planes[1]), nchw(g_planes[2]), nchw(g_lat), None
+
+
+class _Composite(torch.autograd.Function):
+    """volumetric_rendering (helper.py:128-171): (rgb (B,N,3), sigma (B,N,1), t (B,N)) -> comp, acc, weights, bg_lambda, depth."""
+
+    @staticmethod
+    def forward(ctx, rgb, sigma, t, d, far, white, in_sphere):
+        lib = L.load()
+        rgb_c, sig_c = rgb.detach().contiguous().float(), sigma.detach().reshape(sigma.shape[0], -1).contiguous().float()
+        t_c, d_c, far_c = t.detach().contiguous().float(), d.detach().contiguous().float(), far.detach().reshape(-1).contiguous().float()
+        n, N = t_c.shape
+        dev = t_c.device
+        comp, acc = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+        w, depth = torch.empty(n, N, device=dev), torch.empty(n, device=dev)
+        lam = torch.empty(n, 1, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.neo_volumetric_rendering(L.ptr(rgb_c), L.ptr(sig_c), L.ptr(t_c), L.ptr(d_c), L.ptr(far_c), n, N, int(bool(white)),
+                                                 int(bool(in_sphere)), L.ptr(comp), L.ptr(acc), L.ptr(w), L.ptr(lam) if in_sphere else None,
+                                                 L.ptr(depth), _stream()))
+        ctx.save_for_backward(rgb_c, sig_c, t_c, d_c, far_c)
+        ctx.flags = (int(bool(white)), int(bool(in_sphere)))
+        if not in_sphere:
+            lam = torch.zeros(n, 1, device=dev)
+        return comp, acc, w, lam, depth
+
+    @staticmethod
+    def backward(ctx, g_comp, g_acc, g_w, g_lam, g_depth):
+        lib = L.load()
+        rgb_c, sig_c, t_c, d_c, far_c = ctx.saved_tensors
+        white, in_sphere = ctx.flags
+        n, N = t_c.shape
+        dev = t_c.device
+        d_rgb, d_sig = torch.empty(n, N, 3, device=dev), torch.empty(n, N, device=dev)
+        f = lambda g: None if g is None else g.contiguous().float()
+        gs = [f(g_comp), f(g_acc), f(g_w), f(g_lam) if in_sphere else None, f(g_depth)]
+        with torch.cuda.device(dev):
+            L.check(lib.neo_volumetric_rendering_bwd(L.ptr(rgb_c), L.ptr(sig_c), L.ptr(t_c), L.ptr(d_c), L.ptr(far_c), n, N, white, in_sphere,
+                                                     *[L.ptr(g) for g in gs], L.ptr(d_rgb), L.ptr(d_sig), _stream()))
+        return d_rgb, d_sig.reshape(n, N, 1), None, None, None, None, None
+
+
+def _pos_enc(x: Tensor, min_deg: int, max_deg: int) -> Tensor:
+    """helper.py:121-125"""
+    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)], dtype=x.dtype, device=x.device)
+    xb = (x[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], -1)
+    return torch.cat([x, torch.sin(torch.cat([xb, xb + 0.5 * math.pi], -1))], -1)
+
+
+def _world2camera(x: Tensor, c2w: Tensor) -> Tensor:
+    """util.py:52-70: (M,3) world points, (NV,4,4) camera-to-world -> (NV,M,3)."""
+    rot = c2w[:, :3, :3].transpose(1, 2)
+    trans = -torch.bmm(rot, c2w[:, :3, 3:])
+    return torch.matmul(rot[:, None], x[None, :, :, None])[..., 0] + trans[:, None, :, 0]
+
+
+def _world2camera_dirs(v: Tensor, c2w: Tensor) -> Tensor:
+    rot = c2w[:, :3, :3].transpose(1, 2)
+    return torch.matmul(rot[:, None], v[None, :, :, None])[..., 0]
+
+
+def _mlp(mlp, enc: Tensor, dir_tile: Tensor, world: Tensor, local: Tensor, nv: int):
+    """NeRFPPMLP.forward (model.py:110-158): enc (NV,M,63|84), dir_tile (NV*M,27), world (NV*M,128), local (NV*M,512)."""
+    M = enc.shape[1]
+    lin = lambda m, x: F.linear(x, m.weight, m.bias)
+    inp = torch.cat([enc.reshape(-1, enc.shape[-1]), local, world], -1)
+    h = torch.relu(lin(mlp.pts_linears[0], inp))
+    h = torch.relu(lin(mlp.pts_linears[1], h))
+    h = torch.relu(lin(mlp.pts_linears[2], h))
+    h = torch.relu(lin(mlp.pts_linears[3], torch.cat([h, inp], -1)))
+    beta = lin(mlp.bottleneck_layer, h)
+    raw_sigma = lin(mlp.density_layer, h.reshape(nv, M, -1).mean(0))
+    q = lin(mlp.views_linear[0], torch.cat([beta, dir_tile], -1)).reshape(nv, M, -1).mean(0)
+    q = torch.relu(lin(mlp.views_linear[1], torch.relu(q)))
+    return lin(mlp.rgb_layer, q), raw_sigma
+
+
+def render_train(net, rays: Dict[str, Tensor], planes: List[Tensor], latent: Tensor, randomized: bool, white_bkgd: bool,
+                 out_depth: bool = False, uniforms: Optional[List[Tensor]] = None):
+    """NeRF_TP.forward (model.py:266-581, encoder hoisted) with autograd through the MLP parameters, `planes` (xz, xy, yz) and `latent`.
+    `net` must hold a scene built from exactly these feature maps with the fp32 path prepared (`set_scene(..., precisions=["fp32"])`)."""
+    o, d, vd = (rays[k].contiguous().float() for k in ("rays_o", "rays_d", "viewdirs"))
+    if not o.is_cuda:
+        raise RuntimeError("neo360_b200 needs CUDA tensors (no CPU fallback)")
+    B, nv = o.shape[0], net._scene.nv
+    nc, nf = net.num_coarse_samples, net.num_fine_samples
+    poses = rays["src_poses"].float() if "src_poses" in rays else net._scene_inputs[4].float()
+    far = ops.intersect_sphere(o, d)                                            # (B,1); near / far arguments ignored (quirk Q4)
+    near = torch.full_like(far, 1e-4)
+    dirs_cam = _world2camera_dirs(vd, poses)                                     # (NV,B,3)
+    denc = _pos_enc(dirs_cam, 0, 4)                                              # (NV,B,27)
+    u = uniforms if uniforms is not None else [None] * 4
+    mlps = net._mlps()                                                           # fg_coarse, bg_coarse, fg_fine, bg_fine
+    ret = []
+    fg_t = bg_s = fg_w = bg_w = None
+    for level in range(2):
+        if level == 0:
+            fg_t, fg_pts = ops.sample_along_rays(o, d, nc, near, far, randomized, False, True, 3.0, u_rand=u[0])
+            bg_s, bg_pts, bg_lin = ops.sample_along_rays(o, d, nc, near, far, randomized, False, False, 3.0, u_rand=u[1])
+        else:
+            fg_t, fg_pts = ops.sample_pdf(fg_t, fg_w.detach(), o, d, nf, randomized, True, far, 3.0, u_rand=u[2])
+            bg_s, bg_pts, bg_lin = ops.sample_pdf(bg_s, bg_w.detach(), o, d, nf, randomized, False, far, 3.0, u_rand=u[3])
+        N = fg_t.shape[1]
+        dir_tile = denc[:, None].repeat(1, 1, N, 1).reshape(-1, denc.shape[-1])  # quirk Q1: row j sees ray (j mod B)
+        out = []
+        for b, (enc_pts, look_pts, tvals) in enumerate(((fg_pts, fg_pts, fg_t), (bg_pts, bg_lin, bg_s))):
+            cam = _world2camera(enc_pts[..., :3].reshape(-1, 3), poses)          # (NV,B*N,3)
+            if b == 1:
+                cam = torch.cat([cam, enc_pts[..., 3].reshape(1, -1, 1).repeat(nv, 1, 1)], -1)
+            world, local = _Lookup.apply(look_pts.reshape(-1, 3), planes[0], planes[1], planes[2], latent, net)
+            raw_rgb, raw_sigma = _mlp(mlps[2 * level + b], _pos_enc(cam, 0, 10), dir_tile, world, local, nv)
+            sigma = F.softplus(raw_sigma.reshape(B, N, 1) - 1.0)                 # model.py:392-393
+            rgb = torch.sigmoid(raw_rgb.reshape(B, N, 3)) * (1 + 2 * 0.001) - 0.001
+            wb = False if out_depth else white_bkgd                              # model.py:501,519 vs 551,560
+            out.append(_Composite.apply(rgb, sigma, tvals, d, far, wb, b == 0))
+        (fg_c, fg_acc, fg_w, lam, fg_depth), (bg_c, bg_acc, bg_w, _, bg_depth) = out
+        comp = fg_c + lam * bg_c
+        if out_depth:
+            ret.append((comp, fg_c, bg_c, fg_acc, lam, fg_depth + lam.squeeze(-1) * bg_depth))
+        else:
+            fg_m = 0.5 * (fg_t[..., 1:] + fg_t[..., :-1])
+            fg_m = torch.cat([fg_m, (fg_m[:, -1] + (fg_m[:, -1] - fg_m[:, -2]))[:, None]], -1)
+            bg_m = torch.cat([0.5 * (bg_s[..., 1:] + bg_s[..., :-1]), bg_s[..., -1:]], -1)
+            ret.append((comp, fg_w, bg_w, fg_m, bg_m, bg_acc))
+    return ret
+
+
+def distortion_loss(w: Tensor, m: Tensor, interval: Tensor) -> Tensor:
+    """The O(N) form of the regulariser the reference applies through `eff_distloss` (models/neo360/model.py:1246-1260; same functional
+    as the in-tree O(N^2) lossfun_distortion, helper.py:111-118):  1/3 sum_i interval_i w_i^2 + 2 sum_i w_i (m_i W_{<i} - (wm)_{<i})."""
+    loss_uni = (1.0 / 3.0) * (interval * w.pow(2)).sum(-1).mean()
+    wm = w * m
+    w_cum, wm_cum = w.cumsum(-1), wm.cumsum(-1)
+    loss_bi = 2.0 * (wm[..., 1:] * w_cum[..., :-1] - w[..., 1:] * wm_cum[..., :-1]).sum(-1).mean()
+    return loss_uni + loss_bi
+
+
+def training_loss(ret, target: Tensor, dist_weight: float = 0.01) -> Tensor:
+    """MSE of both levels + distortion regulariser on the fine level (model.py:740-748, 1246-1260)."""
+    loss = ((ret[0][0] - target) ** 2).mean() + ((ret[1][0] - target) ** 2).mean()
+    _, fg_w, bg_w, fg_m, bg_m, _ = ret[1]
+    n = fg_w.shape[-1]
+    loss = loss + dist_weight * (distortion_loss(fg_w, fg_m, torch.full_like(fg_w, 1.0 / n)) + distortion_loss(bg_w, bg_m, torch.full_like(bg_w, 1.0 / n)))
+    return loss
+
+
+def allreduce_flat(params, world: int, dist) -> Tensor:
+    """ONE NCCL all-reduce over the flat slab of every parameter gradient (mean over ranks), written back in place."""
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    flat = torch._utils._flatten_dense_tensors(grads)
+    if dist is not None and world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, grads)):
+            p.grad = g.clone() if p.grad is None else p.grad.copy_(g)
+    return flat
+
+
+def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
+    """BASELINE configs[3]: `--batch-rays` rays per step split over the ranks, synthetic NERDS360-shaped scene per rank (encoder out of
+    scope: its outputs are leaf tensors that receive gradients), targets = a fixed random image, Adam + clip 0.05 (model.py:1003-1025)."""
+    import bench as Bm
+    from . import NeRF_TP, synth
+    sc = synth.make_scene((Bm.IMG_W, Bm.IMG_H), Bm.NV, (120, 160), seed=rank)
+    net = NeRF_TP(num_coarse_samples=Bm.N_COARSE, num_fine_samples=Bm.N_FINE, num_src_views=Bm.NV, precision="fp32")
+    net.load_state_dict(synth.make_mlp_params(0))
+    net = net.to(dev).train()
+    maps = {k: sc[k].to(dev).requires_grad_(True) for k in ("planes_xz", "planes_xy", "planes_yz", "latent")}
+    cams = [sc[k].to(dev) for k in ("src_poses", "src_focal", "src_c")]
+    params = [p for m in net._mlps() for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    per = args.batch_rays // world
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = []
+    for s in range(4):
+        o, d = Bm.frame_rays_cpu((7 * s + rank) % 100)
+        sel = torch.randint(0, o.shape[0], (per,), generator=g)
+        host.append((o[sel].contiguous().pin_memory(), d[sel].contiguous().pin_memory(), torch.rand(per, 3, generator=g).pin_memory()))
+    state = {}
+
+    def step(s):
+        o, d, tgt = (x.to(dev, non_blocking=True) for x in host[s % len(host)])
+        net.set_scene(maps["planes_xz"], maps["planes_xy"], maps["planes_yz"], maps["latent"], *cams, sc["img_wh"], precisions=["fp32"])
+        ret = render_train(net, {"rays_o": o, "rays_d": d, "viewdirs": d, "src_poses": cams[0]},
+                           [maps["planes_xz"], maps["planes_xy"], maps["planes_yz"]], maps["latent"], True, False)
+        loss = training_loss(ret, tgt)
+        opt.zero_grad(set_to_none=True)
+        for t in maps.values():
+            t.grad = None
+        loss.backward()
+        flat = allreduce_flat(params, world, dist)
+        torch.nn.utils.clip_grad_norm_(params, 0.05)
+        opt.step()
+        state["loss"] = loss.detach()
+        state["grad_elems"] = flat.numel()
+
+    if sampler:
+        sampler.start()
+    ms = timed(step, args.steps, args.warmup, dev, dist)
+    if sampler:
+        sampler.stop_flag = True
+    loss = float(state["loss"].item())
+    rays = per * world * args.steps
+    return dict(base, metric="training rays/sec, neo360 generalisable training, 4096-ray batches", value=rays / (ms * 1e-3),
+                ms_per_step=ms / args.steps, scaling="strong", dtype="f32",
+                config={"workload": "neo360 training step (BASELINE configs[3]): stratified + PDF sampling, lookups, NeRFPPMLP x4, compositing, "
+                                    "MSE + distortion loss, backward, NCCL gradient all-reduce, clip 0.05, Adam",
+                        "batch_rays": per * world, "rays_per_rank": per, "samples": "128+64", "precision": "fp32 (reference formulation)",
+                        "parallelism": f"data parallel x{world}: one all-reduce over a flat {state['grad_elems']}-element gradient slab per step",
+                        "hand_written": "sampling, lookups fwd/bwd, compositing fwd/bwd", "library": "dense layers (autograd GEMMs), Adam"},
+                e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": per * 9 * 4, "d2h_bytes_per_step": 4},
+                final_loss=loss, clocks=sampler.result() if sampler else None)

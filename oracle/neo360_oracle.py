@@ -167,14 +167,14 @@ def piecewise_constant_pdf(bins: Tensor, w: Tensor, m: int, u_rand: Optional[Ten
 
 def resample_fg(o, d, t_old, w, m, u_rand=None):
     mids = 0.5 * (t_old[..., 1:] + t_old[..., :-1])
-    t_new = piecewise_constant_pdf(mids, w[..., 1:-1], m, u_rand)
+    t_new = piecewise_constant_pdf(mids, w[..., 1:-1], m, u_rand).detach()      # helper.py:222-224: no gradient through the new samples
     t = torch.sort(torch.cat([t_old, t_new], -1), -1).values
     return t, o[:, None, :] + t[..., None] * d[:, None, :]
 
 
 def resample_bg(o, d, s_old, w, m, far, far_unc=3.0, u_rand=None):
     mids = 0.5 * (s_old[..., 1:] + s_old[..., :-1])
-    s_new = piecewise_constant_pdf(mids, w[..., 1:-1], m, u_rand)
+    s_new = piecewise_constant_pdf(mids, w[..., 1:-1], m, u_rand).detach()      # helper.py:222-224
     s = torch.sort(torch.cat([s_old, s_new], -1), -1).values
     t_lin = far * (1.0 - s) + far_unc * s
     s = torch.flip(s, dims=[-1])

@@ -603,3 +603,19 @@ def test_headline_config_vs_oracle(cuda):
                 ps = orc.psnr(got["rgb"].cpu(), ref["comp_rgb"])
                 print(f"headline chunk @{start} [{prec}]: Linf rgb {e_rgb:.2e} acc {e_acc:.2e} depth {e_dep:.2e} PSNR {ps:.1f} dB")
                 assert e_rgb < tol_c and e_acc < tol_c and e_dep < tol_d and ps > db, (prec, start, e_rgb, e_acc, e_dep, ps)
+
+
+def test_output_side_psnr_and_frames(cuda, tmp_path):
+    """PSNR reduced by the library's CUDA kernel equals LitModel.psnr_each (models/interface.py:53-61, oracle.psnr) to
+    1e-4 dB including out-of-range pixels; gather_images at world 1 reshapes ray rows into frames; the writers produce files."""
+    from neo360_b200 import output
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(48 * 64, 3, generator=g) * 1.2 - 0.1
+    b = torch.rand(48 * 64, 3, generator=g)
+    assert abs(output.psnr(a.to(cuda), b.to(cuda)) - orc.psnr(a, b)) < 1e-4
+    assert output.psnr(b.to(cuda), b.to(cuda)) == float("inf")
+    frames = output.gather_images(a.to(cuda), [(48, 64)], 1, 1024)
+    assert frames[0].shape == (48, 64, 3) and md(frames[0].reshape(-1, 3), a) == 0
+    paths = output.store_image(str(tmp_path), frames, "rgb") + output.store_depth_raw(str(tmp_path), [a[:, 0].reshape(48, 64)], "depth")
+    import os
+    assert all(os.path.getsize(p) > 0 for p in paths)
