@@ -47,10 +47,11 @@ def parse():
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="debug: skip the CPU oracle leg (and with it the parity block)")
     ap.add_argument("--no-extras", action="store_true", help="debug: skip the eager-GPU reference leg and the call-pattern variants")
-    ap.add_argument("--mode", default="frames", choices=["frames", "strong", "turntable", "train"],
+    ap.add_argument("--mode", default="frames", choices=["frames", "strong", "turntable", "train", "mip360"],
                     help="frames: BASELINE configs[1], one frame per rank (the headline, default); strong: ONE 640x480 frame split over the ranks "
                          "+ NCCL all-gather of the pixels (models/interface.py:30-50); turntable: BASELINE configs[4], views sharded first; "
-                         "train: BASELINE configs[3], 4096-ray batches with an NCCL gradient all-reduce")
+                         "train: BASELINE configs[3], 4096-ray batches with an NCCL gradient all-reduce; mip360: BASELINE configs[2], "
+                         "Mip-NeRF 360 at 640x480 with 64+64+64 samples, every dense layer on tcgen05")
     ap.add_argument("--views", type=int, default=100, help="turntable mode: number of target views")
     ap.add_argument("--batch-rays", type=int, default=4096, help="train mode: rays per optimisation step over all ranks")
     return ap.parse_args()

@@ -128,6 +128,51 @@ def run(args, rank, world, local, dev, dist, pk):
                             "parallelism": f"views sharded x{world} (view v on rank v mod {world}), no collective"},
                     clocks=sampler.result() if sampler else None)
 
+    if args.mode == "mip360":
+        from neo360_b200 import ops, synth
+        from neo360_b200.mip import MipNeRF360
+        W, H, npp, nn_ = B.IMG_W, B.IMG_H, 64, 64
+        net = MipNeRF360(num_prop_samples=npp, num_nerf_samples=nn_, precision=args.precision).eval()
+        net.load_state_dict(synth.make_mip_params(0))
+        net = net.to(dev)
+        n = min(args.rays, W * H)
+        sub = 16384                                                       # rays per library call (bounds the activation workspace)
+        poses = [synth.target_pose((s * world + rank) % 100, 100)[:3, :4].contiguous().pin_memory() for s in range(4)]
+        out = torch.empty(n, 3).pin_memory()
+
+        def step(s):
+            c2w = poses[s % len(poses)].to(dev, non_blocking=True)
+            ro, vd, rd, rad = ops.get_rays(H, W, 0.8 * W, c2w)
+            with torch.no_grad():
+                for i in range(0, n, sub):
+                    j = min(i + sub, n)
+                    ren, _ = net({"rays_o": ro[i:j], "rays_d": rd[i:j], "viewdirs": vd[i:j], "radii": rad[i:j]}, 1.0, False, False, 0.2, 100.0)
+                    out[i:j].copy_(ren[2]["rgb"], non_blocking=True)
+
+        if sampler:
+            sampler.start()
+        ms = _timed(step, args.steps, args.warmup, dev, dist)
+        if sampler:
+            sampler.stop_flag = True
+        rays = n * world * args.steps
+        # dense-layer MACs per ray: two proposal MLPs 4x256 on 64 samples each, one NeRF MLP 8x1024 (+ heads) on 64
+        prop = 504 * 256 + 3 * 256 * 256 + 256
+        nerf = 504 * 1024 + 6 * 1024 * 1024 + (1024 + 504) * 1024 + 1024 + 1024 * 256 + (256 + 27) * 128 + 128 * 3
+        flop_ray = 2.0 * (2 * npp * prop + nn_ * nerf)
+        ach = rays * flop_ray / (ms * 1e-3) / 1e12
+        return dict(base, metric="rays/sec at 640x480, 192 samples/ray (mipnerf360)", value=rays / (ms * 1e-3), ms_per_step=ms / args.steps,
+                    scaling="weak", dtype="f16 operands, f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
+                    config={"workload": "mipnerf360 unbounded-contraction render, 640x480, 64+64 proposal + 64 NeRF samples (BASELINE configs[2]), "
+                                        "rays generated on the device, rgb copied back to pinned host memory",
+                            "rays_per_step_per_gpu": n, "rays_per_call": sub, "precision": args.precision,
+                            "parallelism": f"one frame per rank x{world}, no collective", "valid_headline": n == W * H},
+                    roofline={"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                              "traffic": None, "peak_source": pk["src"],
+                              "flops": f"{flop_ray / 1e9:.3f} GFLOP/ray of dense layers (2*MAC, padding not counted) over the WHOLE step time "
+                                       "(sampling, IPE features, packing, compositing included)"},
+                    e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 12},
+                    clocks=sampler.result() if sampler else None)
+
     if args.mode == "train":
         from neo360_b200 import training
         return training.bench_train(args, rank, world, local, dev, dist, pk, base, sampler, _timed)

@@ -247,6 +247,8 @@ typedef struct {
     float near_plane, far_plane;   /* near / far passed to MipNeRF360.forward (model.py:236) */
     float train_frac;              /* anneals the proposal logits (model.py:288-292) */
     const float* jitter[3];        /* randomized: one (n_rays) uniform per level (single_jitter, helper.py:357-363); NULL = deterministic */
+    int precision;                 /* NeoPrecision: NEO_PREC_FP32 = fp32 CUDA-core SGEMM chain (tight parity), NEO_PREC_TC = fp16 activations / weights,
+                                      every dense layer on tcgen05 (csrc/gemm_tc.cu) */
 } NeoMipCfg;
 typedef struct {                   /* per level: renderings[l]["rgb"], ray_history[l]{"density","rgb","sdist","weights"} (model.py:359-365) */
     float* rgb[3];       /* (n_rays,3) */
@@ -281,6 +283,10 @@ int neo_tc_selftest_transpose(const float* X, float* outa, float* outb, void* st
  * TMA box load (cp.async.bulk.tensor, 128B swizzle) and multiplied on tcgen05:
  * out0[c][p] = sum_k texel(oy + k/4, ox + k%4)[c] * wt[p][k],  out3 the same for channels 128..255; both (128,64) fp32. */
 int neo_tc_selftest_window(const float* texels, int H, int W, int ox, int oy, const float* wt, float* out0, float* out3, void* stream);
+/* Stage-level entry point of the tensor-core dense layer used by the wide MLPs (csrc/gemm_tc.cu: 2-D TMA tile loads, tcgen05 MMAs,
+ * double-buffered TMEM accumulators): A (M,K), W (N,K) fp32 device, bias (N) or NULL -> out (M,N) fp32 = act(fp16(A) . fp16(W)^T + bias)
+ * rounded to fp16.  K % 64 == 0, N % 64 == 0.  Synchronises the stream (allocates its fp16 staging buffers). */
+int neo_tc_dense(const float* A, const float* W, const float* bias, long long M, int N, int K, int relu, float* out, void* stream);
 /* Host-side view of the TC kernel's encoding-column layout (csrc/field_tc.cu enc_col<>): for in_ch = 3|4 and operand column
  * `col` in [0, KE = 64|96) returns the reference's positional-encoding index (helper.py:121-125 order) in [0, 21*in_ch),
  * -1 for the constant-one (bias) column, -2 for a zero padding column, -3 for invalid arguments.  Pure host code (no GPU). */

@@ -69,7 +69,7 @@ class NeoMipMLPParams(C.Structure):
 
 class NeoMipCfg(C.Structure):
     _fields_ = [("n_prop", C.c_int), ("n_nerf", C.c_int), ("near_plane", C.c_float), ("far_plane", C.c_float), ("train_frac", C.c_float),
-                ("jitter", C.c_void_p * 3)]
+                ("jitter", C.c_void_p * 3), ("precision", C.c_int)]
 
 
 MIP_OUT_FIELDS = ("rgb", "density", "rgb_s", "sdist", "weights")
@@ -110,6 +110,7 @@ SYMBOLS = {
     "neo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "neo_tc_selftest": (C.c_int, [C.c_void_p] * 8),
     "neo_tc_selftest_transpose": (C.c_int, [C.c_void_p] * 4),
+    "neo_tc_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "neo_tc_enc_column": (C.c_int, [C.c_int, C.c_int]),
     "neo_tc_debug": (C.c_int, [C.c_void_p]),
     "neo_tc_selftest_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -6,6 +6,7 @@
 // Structure per level: resample (warp per ray) -> IPE features (warp per sample) -> MLP as a chain of tiled SGEMMs with fused
 // bias/ReLU/concat -> compositing (warp per ray).  This is the validation-grade path for this row (no tensor cores yet).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace neo {
 namespace mip {
@@ -328,14 +329,51 @@ __global__ void composite_kernel(const float* __restrict__ raw_density, const fl
     }
 }
 
+// ---- tensor-core path helpers: out[m][c] = sum_k fp16 h[m][k] * w[c][k] + b[c]  for tiny N (density: 1, rgb: 3); one warp per row ----
+__global__ void rowdot_f16_kernel(const __half* __restrict__ H, long long ld, int K, const float* __restrict__ Wt, const float* __restrict__ b,
+                                  int N, long long M, float* __restrict__ out) {
+    const long long m = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (m >= M) return;
+    const __half* h = H + m * ld;
+    for (int c = 0; c < N; ++c) {
+        float acc = 0.f;
+        for (int k = lane * 8; k < K; k += 256) {
+            const uint4 v = *reinterpret_cast<const uint4*>(h + k);
+            const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hv[i]);
+                acc = fmaf(f.x, __ldg(Wt + (size_t)c * K + k + 2 * i), acc);
+                acc = fmaf(f.y, __ldg(Wt + (size_t)c * K + k + 2 * i + 1), acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[m * N + c] = acc + b[c];
+    }
+}
+
 }  // namespace mip
+// csrc/gemm_tc.cu
+int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* C, long long ldc, long long M, int N, int K,
+             int relu, cudaStream_t s);
+int f32_to_f16_pad(const float* in, long long rows, int cols_in, long long ld_in, void* out, int cols_out, long long ld_out, cudaStream_t s);
 }  // namespace neo
 
 using namespace neo;
 
 namespace {
 struct Cv { float* base; size_t used; float* take(size_t n) { n = (n + 63) & ~size_t(63); float* p = base ? base + used : nullptr; used += n; return p; } };
-struct WSM { float *s[3], *t, *w[3], *X, *Ha, *Hb, *beta, *DE, *V, *rawd, *rawc; };
+struct WSM {
+    float *s[3], *t, *w[3], *X, *Ha, *Hb, *beta, *DE, *V, *rawd, *rawc;
+    // tensor-core path (fp16): two activation buffers [M][width + 512] whose tail columns hold the padded IPE features of buffer 0,
+    // [M][256 + 64] = bottleneck | padded direction encoding, [M][128], and the packed weights
+    void *A16[2], *B16, *V16, *W16;
+};
+constexpr int kFeatPad = 512, kDirPad = 64;
+size_t tc_weight_halves(int width) {      // fp16 elements of one MLP's packed weights (upper bound: the 8-layer NeRF MLP)
+    return (size_t)width * kFeatPad + 6 * (size_t)width * width + (size_t)width * (width + kFeatPad) + 256 * (size_t)width + 128 * (256 + kDirPad);
+}
 size_t carve(Cv& c, int n, const NeoMipCfg* cfg, int width, WSM& w) {
     const int ns[3] = {cfg->n_prop, cfg->n_prop, cfg->n_nerf};
     int nmax = cfg->n_prop > cfg->n_nerf ? cfg->n_prop : cfg->n_nerf;
@@ -343,20 +381,88 @@ size_t carve(Cv& c, int n, const NeoMipCfg* cfg, int width, WSM& w) {
     w.t = c.take((size_t)n * (nmax + 1));
     const size_t M = (size_t)n * nmax;
     w.X = c.take(M * mip::kFeat);
-    w.Ha = c.take(M * width); w.Hb = c.take(M * width);
-    w.beta = c.take(M * 256); w.DE = c.take(M * 27); w.V = c.take(M * 128);
+    const bool tcp = cfg->precision == NEO_PREC_TC;          // the fp32 activation buffers are not needed on the tensor-core path
+    w.Ha = c.take(tcp ? 0 : M * width); w.Hb = c.take(tcp ? 0 : M * width);
+    w.beta = c.take(tcp ? 0 : M * 256); w.DE = c.take(M * 27); w.V = c.take(tcp ? 0 : M * 128);
     w.rawd = c.take(M); w.rawc = c.take(M * 3);
+    if (cfg->precision == NEO_PREC_TC) {
+        for (int i = 0; i < 2; ++i) w.A16[i] = c.take((M * (size_t)(width + kFeatPad) + 1) / 2);
+        w.B16 = c.take((M * (256 + kDirPad) + 1) / 2);
+        w.V16 = c.take((M * 128 + 1) / 2);
+        w.W16 = c.take((tc_weight_halves(width) + 1) / 2);
+    }
     return c.used * sizeof(float);
 }
 int check(const NeoMipCfg* c) {
     if (!c || c->n_prop < 2 || c->n_nerf < 2 || c->n_prop > 160 || c->n_nerf > 160) { set_error("mip: sample counts must be in [2,160]"); return NEO_ERR_INVALID; }
     if (!(c->near_plane > 0.f) || !(c->far_plane > c->near_plane)) { set_error("mip: need 0 < near < far"); return NEO_ERR_INVALID; }
+    if (c->precision != NEO_PREC_FP32 && c->precision != NEO_PREC_TC) { set_error("mip: bad precision %d", c->precision); return NEO_ERR_INVALID; }
     return NEO_OK;
 }
 int gemm(const float* A1, int K1, const float* A2, int K2, const float* W, const float* b, long long M, int N, int relu, float* out, cudaStream_t s) {
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
     mip::sgemm_kernel<<<grid, 256, 0, s>>>(A1, K1, A2, K2, W, b, M, N, relu, out);
     NEO_LAUNCH_CHECK("mip sgemm_kernel");
+    return NEO_OK;
+}
+
+// One MLP of Mip-NeRF 360 (models/mipnerf360/model.py:30-195) on tensor cores: fp16 activations, every dense layer a gemm_f16 launch
+// (csrc/gemm_tc.cu), the skip concatenation by laying h4 and the features out in ONE buffer (layer 5 is a single K = width + 512 GEMM).
+int mlp_tc(const NeoMipMLPParams& p, const WSM& w, long long M, int n, const float* viewdirs, float* rawd, float* rawc, cudaStream_t s) {
+    const int W = p.width, ld = W + kFeatPad;
+    if (W % 64) { set_error("mip tc: width must be a multiple of 64 (got %d)", W); return NEO_ERR_UNSUPPORTED; }
+    __half* buf[2] = {(__half*)w.A16[0], (__half*)w.A16[1]};
+    __half* wp = (__half*)w.W16;
+    int rc;
+    // features (fp32, [M][504]) -> tail columns of buffer 0, zero padded to 512
+    if ((rc = f32_to_f16_pad(w.X, M, mip::kFeat, mip::kFeat, buf[0] + W, kFeatPad, ld, s))) return rc;
+    auto pack = [&](const float* src, int rows, int cols_in, int cols_out) -> __half* {
+        __half* dst = wp;
+        wp += (size_t)rows * cols_out;
+        return f32_to_f16_pad(src, rows, cols_in, cols_in, dst, cols_out, cols_out, s) ? nullptr : dst;
+    };
+    __half* w0 = pack(p.w[0], W, mip::kFeat, kFeatPad);
+    if (!w0) return NEO_ERR_CUDA;
+    if ((rc = gemm_f16(buf[0] + W, ld, w0, kFeatPad, p.b[0], buf[0], ld, M, W, kFeatPad, 1, s))) return rc;
+    for (int l = 1; l < p.depth; ++l) {
+        const bool skip_in = (l == 5);                      // cat([h, inputs]) after layer 4 feeds layer 5 (model.py:122-128)
+        __half* wl;
+        int K;
+        if (skip_in) {
+            // W5 is (width, width + 504): columns [0, width) stay, the 504 feature columns are padded to 512
+            wl = wp;
+            wp += (size_t)W * (W + kFeatPad);
+            if ((rc = f32_to_f16_pad(p.w[l], W, W, W + mip::kFeat, wl, W, W + kFeatPad, s))) return rc;
+            if ((rc = f32_to_f16_pad(p.w[l] + W, W, mip::kFeat, W + mip::kFeat, wl + W, kFeatPad, W + kFeatPad, s))) return rc;
+            K = W + kFeatPad;
+        } else {
+            wl = pack(p.w[l], W, W, W);
+            if (!wl) return NEO_ERR_CUDA;
+            K = W;
+        }
+        if ((rc = gemm_f16(buf[(l - 1) & 1], ld, wl, K, p.b[l], buf[l & 1], ld, M, W, K, 1, s))) return rc;
+    }
+    const __half* h = buf[(p.depth - 1) & 1];
+    mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h, ld, W, p.wsig, p.bsig, 1, M, rawd);
+    NEO_LAUNCH_CHECK("mip rowdot_f16_kernel(density)");
+    if (p.wrgb) {
+        __half* B = (__half*)w.B16;
+        __half* V = (__half*)w.V16;
+        const int ldb = 256 + kDirPad;
+        __half* wb = pack(p.wb, 256, W, W);
+        if (!wb) return NEO_ERR_CUDA;
+        if ((rc = gemm_f16(h, ld, wb, W, p.bb, B, ldb, M, 256, W, 0, s))) return rc;
+        mip::dir_kernel<<<(unsigned)((M * 27 + 255) / 256), 256, 0, s>>>(viewdirs, M, n, w.DE);
+        NEO_LAUNCH_CHECK("mip dir_kernel");
+        if ((rc = f32_to_f16_pad(w.DE, M, 27, 27, B + 256, kDirPad, ldb, s))) return rc;
+        __half* wv = wp;
+        wp += (size_t)128 * ldb;
+        if ((rc = f32_to_f16_pad(p.wv0, 128, 256, 256 + 27, wv, 256, ldb, s))) return rc;
+        if ((rc = f32_to_f16_pad(p.wv0 + 256, 128, 27, 256 + 27, wv + 256, kDirPad, ldb, s))) return rc;
+        if ((rc = gemm_f16(B, ldb, wv, ldb, p.bv0, V, 128, M, 128, ldb, 1, s))) return rc;
+        mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(V, 128, 128, p.wrgb, p.brgb, 3, M, rawc);
+        NEO_LAUNCH_CHECK("mip rowdot_f16_kernel(rgb)");
+    }
     return NEO_OK;
 }
 }  // namespace
@@ -405,25 +511,31 @@ extern "C" int neo_mip_render_fwd(const NeoMipMLPParams mlps[3], const float* ra
         mip::features_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(rays_o, rays_d, radii, w.t, mlps[lvl].basis, M, n, w.X);
         NEO_LAUNCH_CHECK("mip features_kernel");
         const NeoMipMLPParams& p = mlps[lvl];
-        float* src = w.Ha;
-        float* dst = w.Hb;
-        if ((rc = gemm(w.X, mip::kFeat, nullptr, 0, p.w[0], p.b[0], M, p.width, 1, src, s))) return rc;
-        for (int l = 1; l < p.depth; ++l) {
-            const bool skip_in = (l == 5);                      // cat([h, inputs]) after layer 4 feeds layer 5
-            if ((rc = gemm(src, p.width, skip_in ? w.X : nullptr, skip_in ? mip::kFeat : 0, p.w[l], p.b[l], M, p.width, 1, dst, s))) return rc;
-            float* tmp = src; src = dst; dst = tmp;
-        }
-        if ((rc = gemm(src, p.width, nullptr, 0, p.wsig, p.bsig, M, 1, 0, w.rawd, s))) return rc;
         const float* rawc = nullptr;
-        if (p.wrgb) {
-            if ((rc = gemm(src, p.width, nullptr, 0, p.wb, p.bb, M, 256, 0, w.beta, s))) return rc;
-            mip::dir_kernel<<<(unsigned)((M * 27 + 255) / 256), 256, 0, s>>>(viewdirs, M, n, w.DE);
-            NEO_LAUNCH_CHECK("mip dir_kernel");
-            if ((rc = gemm(w.beta, 256, w.DE, 27, p.wv0, p.bv0, M, 128, 1, w.V, s))) return rc;
-            if ((rc = gemm(w.V, 128, nullptr, 0, p.wrgb, p.brgb, M, 3, 0, w.rawc, s))) return rc;
-            rawc = w.rawc;
+        if (cfg->precision == NEO_PREC_TC) {
+            if ((rc = mlp_tc(p, w, M, n, viewdirs, w.rawd, w.rawc, s))) return rc;
+            if (p.wrgb) rawc = w.rawc;
+            else if (out->rgb_s[lvl]) NEO_CUDA(cudaMemsetAsync(out->rgb_s[lvl], 0, (size_t)M * 3 * sizeof(float), s));
         } else {
-            if (out->rgb_s[lvl]) NEO_CUDA(cudaMemsetAsync(out->rgb_s[lvl], 0, (size_t)M * 3 * sizeof(float), s));     // disable_rgb: zeros
+            float* src = w.Ha;
+            float* dst = w.Hb;
+            if ((rc = gemm(w.X, mip::kFeat, nullptr, 0, p.w[0], p.b[0], M, p.width, 1, src, s))) return rc;
+            for (int l = 1; l < p.depth; ++l) {
+                const bool skip_in = (l == 5);                      // cat([h, inputs]) after layer 4 feeds layer 5
+                if ((rc = gemm(src, p.width, skip_in ? w.X : nullptr, skip_in ? mip::kFeat : 0, p.w[l], p.b[l], M, p.width, 1, dst, s))) return rc;
+                float* tmp = src; src = dst; dst = tmp;
+            }
+            if ((rc = gemm(src, p.width, nullptr, 0, p.wsig, p.bsig, M, 1, 0, w.rawd, s))) return rc;
+                    if (p.wrgb) {
+                if ((rc = gemm(src, p.width, nullptr, 0, p.wb, p.bb, M, 256, 0, w.beta, s))) return rc;
+                mip::dir_kernel<<<(unsigned)((M * 27 + 255) / 256), 256, 0, s>>>(viewdirs, M, n, w.DE);
+                NEO_LAUNCH_CHECK("mip dir_kernel");
+                if ((rc = gemm(w.beta, 256, w.DE, 27, p.wv0, p.bv0, M, 128, 1, w.V, s))) return rc;
+                if ((rc = gemm(w.V, 128, nullptr, 0, p.wrgb, p.brgb, M, 3, 0, w.rawc, s))) return rc;
+                rawc = w.rawc;
+            } else {
+                if (out->rgb_s[lvl]) NEO_CUDA(cudaMemsetAsync(out->rgb_s[lvl], 0, (size_t)M * 3 * sizeof(float), s));     // disable_rgb: zeros
+            }
         }
         const int cw = 8;
         mip::composite_kernel<<<(n_rays + cw - 1) / cw, cw * 32, 0, s>>>(w.rawd, rawc, w.t, rays_d, n_rays, n, out->density[lvl],

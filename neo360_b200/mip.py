@@ -62,8 +62,10 @@ class PropMLP(MipNeRF360MLP):
 
 
 class MipNeRF360(nn.Module):
-    def __init__(self, num_prop_samples: int = 64, num_nerf_samples: int = 32, num_levels: int = 3, **reference_defaults):
+    def __init__(self, num_prop_samples: int = 64, num_nerf_samples: int = 32, num_levels: int = 3, precision: str = "fp32",
+                 **reference_defaults):
         super().__init__()
+        self.precision = precision          # "fp32": CUDA-core SGEMM chain (tight parity); "tc": every dense layer on tcgen05 (fp16 operands)
         if num_levels != 3 or reference_defaults:
             raise NotImplementedError("reference defaults only (models/mipnerf360/model.py:199-223)")
         self.num_prop_samples, self.num_nerf_samples = num_prop_samples, num_nerf_samples
@@ -85,6 +87,7 @@ class MipNeRF360(nn.Module):
         cfg = L.NeoMipCfg()
         cfg.n_prop, cfg.n_nerf = self.num_prop_samples, self.num_nerf_samples
         cfg.near_plane, cfg.far_plane, cfg.train_frac = float(near), float(far), float(train_frac)
+        cfg.precision = {"fp32": L.NEO_PREC_FP32, "tc": L.NEO_PREC_TC}[self.precision]
         if randomized:
             jit = batch.get("_uniforms") or [torch.rand((n, 1), device=dev) for _ in range(3)]     # helper.py:361 (single_jitter)
             for i in range(3):

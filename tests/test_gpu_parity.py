@@ -438,6 +438,31 @@ def test_mip360_vs_reference_vectors(cuda, tag):
         close(ren_r[i]["rgb"], g[f"{tag}_rand{i}_rgb"], (i, "rendering rand"))
 
 
+@pytest.mark.parametrize("tag", ["m_tiny", "m_small"])
+def test_mip360_tc_vs_reference_vectors(cuda, tag):
+    """Mip-NeRF 360 with every dense layer on tcgen05 (NEO_PREC_TC: fp16 weights / activations, fp32 accumulate, csrc/gemm_tc.cu) against
+    outputs of the UNMODIFIED reference module.  Stated: level-0 sample positions exact (no MLP upstream); renderings L-inf <= 3e-2 and
+    PSNR >= 35 dB per level; fp32 CUDA path of the same weights within the same bound (it is itself within 2e-4 of the reference)."""
+    import os
+    from neo360_b200.mip import MipNeRF360
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mip360_reference_vectors.npz"))
+    W, H, B, npp, nn_, seed = [int(x) for x in g[f"{tag}_cfg"]]
+    near, far = [float(x) for x in g[f"{tag}_near_far"]]
+    net = MipNeRF360(num_prop_samples=npp, num_nerf_samples=nn_, precision="tc").eval()
+    net.load_state_dict(synth.make_mip_params(seed))
+    net = net.to(cuda)
+    batch = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs", "radii")}
+    with torch.no_grad():
+        ren, hist = net(batch, 1.0, False, False, near, far)
+    torch.cuda.synchronize()
+    assert md(hist[0]["sdist"], T(g[f"{tag}_hist0_sdist"])) < 2e-5
+    for i in range(3):
+        err = md(ren[i]["rgb"], T(g[f"{tag}_eval{i}_rgb"]))
+        ps = orc.psnr(ren[i]["rgb"].cpu(), T(g[f"{tag}_eval{i}_rgb"]))
+        print(f"mip tc [{tag}] level {i}: rendering L-inf {err:.2e}, PSNR {ps:.1f} dB")
+        assert err < 3e-2 and ps > 35.0, (i, err, ps)
+
+
 # ---------------- edge cases of the NeO-360 path ----------------
 
 def _frame_rays(W, H, view=3):
@@ -619,3 +644,24 @@ def test_output_side_psnr_and_frames(cuda, tmp_path):
     paths = output.store_image(str(tmp_path), frames, "rgb") + output.store_depth_raw(str(tmp_path), [a[:, 0].reshape(48, 64)], "depth")
     import os
     assert all(os.path.getsize(p) > 0 for p in paths)
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(1000, 1024, 512, 1), (257, 256, 1536, 1), (4096, 128, 320, 1), (130, 64, 64, 0), (70000, 1024, 1024, 1)])
+def test_tc_dense_vs_torch(cuda, M, N, K, relu):
+    """The tensor-core dense layer of the wide MLPs (csrc/gemm_tc.cu: TMA tile loads + tcgen05, fp16 operands, fp32 accumulate) against a
+    plain PyTorch fp32 reference of the same op on the fp16-rounded operands; ragged M, every N tile width (64/128/256), K up to 1536.
+    Stated: |err| <= 2e-3 * max|ref| (fp32 accumulation order + the fp16 rounding of the output)."""
+    from neo360_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    out = torch.empty(M, N, device=cuda)
+    L.check(lib.neo_tc_dense(L.ptr(A), L.ptr(W), L.ptr(b), M, N, K, relu, L.ptr(out), torch.cuda.current_stream().cuda_stream))
+    ref = A.half().float() @ W.half().float().T + b
+    if relu:
+        ref = torch.relu(ref)
+    err = float((out - ref).abs().max())
+    print(f"tc dense {M}x{N}x{K}: max err {err:.3e}, max ref {float(ref.abs().max()):.3f}")
+    assert err <= 2e-3 * float(ref.abs().max())
