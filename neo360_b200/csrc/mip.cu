@@ -161,7 +161,7 @@ __global__ void resample_kernel(const float* __restrict__ s_prev, const float* _
 // ------------------------------------------------------------------------------------------------
 __global__ void features_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ radii,
                                 const float* __restrict__ tdist, const float* __restrict__ basis, long long M, int n,
-                                float* __restrict__ X) {
+                                float* __restrict__ X, __half* __restrict__ X16, long long ld16) {
     const long long m = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (m >= M) return;
@@ -200,18 +200,49 @@ __global__ void features_kernel(const float* __restrict__ rays_o, const float* _
         float cp[3];
         for (int i = 0; i < 3; ++i) cp[i] = zc[i][0] * p[0] + zc[i][1] * p[1] + zc[i][2] * p[2];
         const float lv = p[0] * cp[0] + p[1] * cp[1] + p[2] * cp[2];
-        float* x = X + (size_t)m * kFeat;
         float sc = 1.f;
-        for (int kk = 0; kk < kDeg; ++kk) {
-            const float sm_ = lm * sc, e = expf(-0.5f * (lv * sc * sc));
-            x[kk * kBasis + lane] = e * sinf(sm_);
-            x[kDeg * kBasis + kk * kBasis + lane] = e * sinf(sm_ + 1.57079637f);
-            sc *= 2.f;
+        if (X16) {          // tensor-core path: fp16 row of the activation buffer (row stride ld16), columns 504..511 zero padded below
+            __half* x = X16 + (size_t)m * ld16;
+            for (int kk = 0; kk < kDeg; ++kk) {
+                const float sm_ = lm * sc, e = expf(-0.5f * (lv * sc * sc));
+                x[kk * kBasis + lane] = __float2half_rn(e * sinf(sm_));
+                x[kDeg * kBasis + kk * kBasis + lane] = __float2half_rn(e * sinf(sm_ + 1.57079637f));
+                sc *= 2.f;
+            }
+        } else {
+            float* x = X + (size_t)m * kFeat;
+            for (int kk = 0; kk < kDeg; ++kk) {
+                const float sm_ = lm * sc, e = expf(-0.5f * (lv * sc * sc));
+                x[kk * kBasis + lane] = e * sinf(sm_);
+                x[kDeg * kBasis + kk * kBasis + lane] = e * sinf(sm_ + 1.57079637f);
+                sc *= 2.f;
+            }
         }
+    } else if (X16 && lane < kBasis + 8) {
+        X16[(size_t)m * ld16 + kFeat + (lane - kBasis)] = __float2half_rn(0.f);
     }
 }
 
 // direction encoding broadcast to samples: DE[m][27]
+__global__ void dir16_kernel(const float* __restrict__ viewdirs, long long M, int n, __half* __restrict__ out, long long ld, int pad) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= M * pad) return;
+    const long long m = gid / pad;
+    const int c = (int)(gid % pad);
+    float val = 0.f;
+    if (c < 27) {
+        const float* d = viewdirs + 3 * (m / n);
+        if (c < 3) val = d[c];
+        else {
+            int q = c - 3;
+            const bool shifted = q >= 12;
+            if (shifted) q -= 12;
+            const float xb = mul_(d[q % 3], (float)(1 << (q / 3)));
+            val = sinf(shifted ? add_(xb, 1.57079637f) : xb);
+        }
+    }
+    out[m * ld + c] = __float2half_rn(val);
+}
 __global__ void dir_kernel(const float* __restrict__ viewdirs, long long M, int n, float* __restrict__ DE) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= M * 27) return;
@@ -380,10 +411,10 @@ size_t carve(Cv& c, int n, const NeoMipCfg* cfg, int width, WSM& w) {
     for (int l = 0; l < 3; ++l) { w.s[l] = c.take((size_t)n * (ns[l] + 1)); w.w[l] = c.take((size_t)n * ns[l]); }
     w.t = c.take((size_t)n * (nmax + 1));
     const size_t M = (size_t)n * nmax;
-    w.X = c.take(M * mip::kFeat);
     const bool tcp = cfg->precision == NEO_PREC_TC;          // the fp32 activation buffers are not needed on the tensor-core path
+    w.X = c.take(tcp ? 0 : M * mip::kFeat);
     w.Ha = c.take(tcp ? 0 : M * width); w.Hb = c.take(tcp ? 0 : M * width);
-    w.beta = c.take(tcp ? 0 : M * 256); w.DE = c.take(M * 27); w.V = c.take(tcp ? 0 : M * 128);
+    w.beta = c.take(tcp ? 0 : M * 256); w.DE = c.take(tcp ? 0 : M * 27); w.V = c.take(tcp ? 0 : M * 128);
     w.rawd = c.take(M); w.rawc = c.take(M * 3);
     if (cfg->precision == NEO_PREC_TC) {
         for (int i = 0; i < 2; ++i) w.A16[i] = c.take((M * (size_t)(width + kFeatPad) + 1) / 2);
@@ -414,8 +445,7 @@ int mlp_tc(const NeoMipMLPParams& p, const WSM& w, long long M, int n, const flo
     __half* buf[2] = {(__half*)w.A16[0], (__half*)w.A16[1]};
     __half* wp = (__half*)w.W16;
     int rc;
-    // features (fp32, [M][504]) -> tail columns of buffer 0, zero padded to 512
-    if ((rc = f32_to_f16_pad(w.X, M, mip::kFeat, mip::kFeat, buf[0] + W, kFeatPad, ld, s))) return rc;
+    // the IPE features were written by features_kernel as fp16 into the tail columns of buffer 0 (zero padded to 512)
     auto pack = [&](const float* src, int rows, int cols_in, int cols_out) -> __half* {
         __half* dst = wp;
         wp += (size_t)rows * cols_out;
@@ -452,9 +482,8 @@ int mlp_tc(const NeoMipMLPParams& p, const WSM& w, long long M, int n, const flo
         __half* wb = pack(p.wb, 256, W, W);
         if (!wb) return NEO_ERR_CUDA;
         if ((rc = gemm_f16(h, ld, wb, W, p.bb, B, ldb, M, 256, W, 0, s))) return rc;
-        mip::dir_kernel<<<(unsigned)((M * 27 + 255) / 256), 256, 0, s>>>(viewdirs, M, n, w.DE);
-        NEO_LAUNCH_CHECK("mip dir_kernel");
-        if ((rc = f32_to_f16_pad(w.DE, M, 27, 27, B + 256, kDirPad, ldb, s))) return rc;
+        mip::dir16_kernel<<<(unsigned)((M * kDirPad + 255) / 256), 256, 0, s>>>(viewdirs, M, n, B + 256, ldb, kDirPad);
+        NEO_LAUNCH_CHECK("mip dir16_kernel");
         __half* wv = wp;
         wp += (size_t)128 * ldb;
         if ((rc = f32_to_f16_pad(p.wv0, 128, 256, 256 + 27, wv, 256, ldb, s))) return rc;
@@ -508,7 +537,9 @@ extern "C" int neo_mip_render_fwd(const NeoMipMLPParams mlps[3], const float* ra
                                                                                    cfg->jitter[lvl], w.s[lvl], w.t, p2);
         NEO_LAUNCH_CHECK("mip resample_kernel");
         const long long M = (long long)n_rays * n;
-        mip::features_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(rays_o, rays_d, radii, w.t, mlps[lvl].basis, M, n, w.X);
+        const bool tcp = cfg->precision == NEO_PREC_TC;
+        mip::features_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(rays_o, rays_d, radii, w.t, mlps[lvl].basis, M, n, w.X,
+                                                                    tcp ? (__half*)w.A16[0] + mlps[lvl].width : nullptr, mlps[lvl].width + kFeatPad);
         NEO_LAUNCH_CHECK("mip features_kernel");
         const NeoMipMLPParams& p = mlps[lvl];
         const float* rawc = nullptr;
