@@ -136,7 +136,7 @@ def run(args, rank, world, local, dev, dist, pk):
         net.load_state_dict(synth.make_mip_params(0))
         net = net.to(dev)
         n = min(args.rays, W * H)
-        sub = 16384                                                       # rays per library call (bounds the activation workspace)
+        sub = 65536                                                       # rays per library call (bounds the activation workspace: ~26 GB)
         poses = [synth.target_pose((s * world + rank) % 100, 100)[:3, :4].contiguous().pin_memory() for s in range(4)]
         out = torch.empty(n, 3).pin_memory()
 

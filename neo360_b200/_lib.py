@@ -127,7 +127,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("NEO360_B200_LIB", LIB_PATH)      # override: A/B runs of experimental kernel builds (tools/)
+    path = os.environ.get("NEO360_B200_LIB") or LIB_PATH      # override: A/B runs of experimental kernel builds (tools/)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -m neo360_b200.build` (or __graft_entry__.build()); "
                            "there is no CPU fallback")

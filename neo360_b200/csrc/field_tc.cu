@@ -38,6 +38,9 @@ namespace tc {
 // 18 warps: 0-3 epilogue set A (block 0 + colour head), 4-7 epilogue set B (block 1), 8 MMA issue, 9-12 geometry, 13-16 texel windows
 // (one map each: latent, xz, xy, yz), 17 points + direction encoding.  Every hand-off is an mbarrier: the roles run decoupled, as far
 // ahead as their double-buffered slots and the window ring allow.  (5 warps on two of the four schedulers => 96 registers/thread.)
+#ifndef NEO_TRUNK_N64
+#define NEO_TRUNK_N64 1
+#endif
 #ifndef NEO_WIN_WARPS
 #define NEO_WIN_WARPS 4
 #endif
@@ -1185,6 +1188,29 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                         }
                         whead += nwin;
                         if (lane == 0) TRACE(3, kcount, 2, 0);
+#if NEO_TRUNK_N64
+                        // one N = 64 MMA per k-step covers both 32-point blocks (a tcgen05.mma costs the issuing warp ~40 cycles whatever its
+                        // size): half the instructions per layer; the two epilogue sets still convert their halves concurrently
+                        const uint32_t id_half_mn = idesc_f16(128, 64, 0, 1);
+                        for (int l = 1; l <= 3; ++l) {
+                            const uint32_t aW = (l == 1) ? aW1 : (l == 2 ? aW2 : aW3h);
+                            wait_h(0, 11);                          // layer l-1 of both blocks is in H
+                            wait_h(1, 11);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    mma_ts((l == 3 ? dD3 : dD), aW + ks * 8, dHb[0] + (uint64_t)(ks * (2048 >> 4)), id_half_mn, (l == 3) || ks > 0);
+                                if (l < 3) {
+                                    mma_ts(dD, aB, dSEL + (uint64_t)(2 * l), id_blk, 1);          // + b_l  (b0, b3: ENC constant column)
+                                    mma_ts(dD + 32, aB, dSEL + (uint64_t)(2 * l), id_blk, 1);
+                                }
+                                tc_commit(BAR(ACC_READY));
+                                tc_commit(BAR(ACC_READY + 1));
+                            }
+                            __syncwarp();
+                            if (pend && v == 0 && h == 0 && l < 3) color_stage(l - 1);
+                        }
+#else
                         for (int l = 1; l <= 3; ++l) {
                             const uint32_t aW = (l == 1) ? aW1 : (l == 2 ? aW2 : aW3h);
                             for (int bb = 0; bb < 2; ++bb) {
@@ -1200,6 +1226,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_tc_kernel(const __grid_cons
                             }
                             if (pend && v == 0 && h == 0 && l < 3) color_stage(l - 1);
                         }
+#endif
                         if (lane == 0) TRACE(3, kcount, 3, 0);
                         wait_h(0, 13);                              // h3 of both blocks written
                         wait_h(1, 13);

@@ -665,3 +665,47 @@ def test_tc_dense_vs_torch(cuda, M, N, K, relu):
     err = float((out - ref).abs().max())
     print(f"tc dense {M}x{N}x{K}: max err {err:.3e}, max ref {float(ref.abs().max()):.3f}")
     assert err <= 2e-3 * float(ref.abs().max())
+
+
+def test_scene_cache_is_keyed_by_identity_and_parameter_version(cuda):
+    """(1) a new scene whose tensors the caching allocator placed at the SAME addresses as the freed previous scene must
+    not be rendered with the previous scene's packed maps; (2) a parameter update after the first render must be picked up (the scene
+    packs the weights).  Both against the oracle (fp32 path, 2e-4)."""
+    from neo360_b200 import NeRF_TP
+    W, H, nc, nf = 48, 36, 12, 6
+    P = synth.make_mlp_params(3)
+    net = NeRF_TP(num_coarse_samples=nc, num_fine_samples=nf, precision="fp32").eval()
+    net.load_state_dict(P)
+    net = net.to(cuda)
+    rays = {k: v[300:300 + 40].contiguous() for k, v in _frame_rays(W, H).items()}
+    cr = {k: v.to(cuda) for k, v in rays.items()}
+    ptrs = []
+    for seed in (11, 12):
+        sc = synth.make_scene((W, H), 3, (18, 24), seed)
+        batch = dict(cr)
+        batch.update({k: sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")})
+        batch["src_imgs"] = torch.zeros(3, 3, H, W, device=cuda)
+        ptrs.append(batch["latent"].data_ptr())
+        osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                        float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+        with torch.no_grad():
+            got = net(batch, False, False, None, None, out_depth=True)[1]
+            ref = orc.render(rays, osc, P, nc, nf, False, True)[1]
+        net.check()
+        assert md(got[0], ref[0]) < 2e-4, (seed, md(got[0], ref[0]))
+        del batch, sc                                        # free the scene tensors: the next scene reuses the blocks
+        torch.cuda.synchronize()
+    print("latent addresses of the two scenes:", ptrs, "(equal = the allocator reused the block)")
+    # (2) in-place parameter update: the packed weights must be rebuilt
+    sc = synth.make_scene((W, H), 3, (18, 24), 13)
+    net.set_scene(*[sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")], sc["img_wh"])
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+    with torch.no_grad():
+        a = net(cr, False, False, None, None, out_depth=True)[1][0]
+        P2 = {k: v.clone() for k, v in synth.make_mlp_params(4).items()}
+        net.load_state_dict(P2)                              # copies in place: same storages, new versions
+        b = net(cr, False, False, None, None, out_depth=True)[1][0]
+        ref2 = orc.render(rays, osc, P2, nc, nf, False, True)[1][0]
+    net.check()
+    assert md(a, b) > 1e-3 and md(b, ref2) < 2e-4, (md(a, b), md(b, ref2))
