@@ -173,6 +173,46 @@ def run(args, rank, world, local, dev, dist, pk):
                     e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 12},
                     clocks=sampler.result() if sampler else None)
 
+    if args.mode == "vanilla":
+        from neo360_b200 import ops, synth
+        from neo360_b200.vanilla import NeRF
+        W, H, nc, nf = B.IMG_W, B.IMG_H, 64, 128                          # reference defaults (models/vanilla_nerf/model.py:135-136): 65 + 193 points per ray
+        net = NeRF(num_coarse_samples=nc, num_fine_samples=nf).eval()
+        net.precision = args.precision
+        net.load_state_dict(synth.make_vanilla_params(0))
+        net = net.to(dev)
+        n, sub = min(args.rays, W * H), 65536
+        poses = [synth.target_pose((s * world + rank) % 100, 100)[:3, :4].contiguous().pin_memory() for s in range(4)]
+        out = torch.empty(n, 3).pin_memory()
+
+        def step(s):
+            c2w = poses[s % len(poses)].to(dev, non_blocking=True)
+            ro, vd, rd, _ = ops.get_rays(H, W, 0.8 * W, c2w)
+            with torch.no_grad():
+                for i in range(0, n, sub):
+                    j = min(i + sub, n)
+                    ev = net({"rays_o": ro[i:j], "rays_d": rd[i:j], "viewdirs": vd[i:j]}, False, True, 0.2, 3.0)
+                    out[i:j].copy_(ev[1][0], non_blocking=True)
+
+        if sampler:
+            sampler.start()
+        ms = _timed(step, args.steps, args.warmup, dev, dist)
+        if sampler:
+            sampler.stop_flag = True
+        rays = n * world * args.steps
+        flop_ray = 2.0 * 593408 * ((nc + 1) + (nc + 1 + nf))               # 593 408 MAC per point
+        ach = rays * flop_ray / (ms * 1e-3) / 1e12
+        return dict(base, metric="rays/sec at 640x480, vanilla NeRF 64+128 samples", value=rays / (ms * 1e-3), ms_per_step=ms / args.steps,
+                    scaling="weak", dtype="f16 operands, f32 accumulate (tcgen05)" if args.precision == "tc" else "f32",
+                    config={"workload": "vanilla NeRF two-level render, 640x480, 64 + 128 samples (65 + 193 points per ray), rays generated on the device",
+                            "rays_per_step_per_gpu": n, "rays_per_call": sub, "precision": args.precision,
+                            "parallelism": f"one frame per rank x{world}, no collective", "valid_headline": n == W * H},
+                    roofline={"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                              "traffic": None, "peak_source": pk["src"],
+                              "flops": f"{flop_ray / 1e6:.1f} MFLOP/ray of dense layers (2*MAC) over the WHOLE step time"},
+                    e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 12},
+                    clocks=sampler.result() if sampler else None)
+
     if args.mode == "train":
         from neo360_b200 import training
         return training.bench_train(args, rank, world, local, dev, dist, pk, base, sampler, _timed)

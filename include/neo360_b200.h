@@ -213,6 +213,8 @@ typedef struct {
     float near_plane, far_plane;   /* the scalar near / far the caller passes to NeRF.forward (model.py:154) */
     const float* u0;               /* randomized: (n_rays, n_coarse+1) uniforms, helper.py:438; NULL = deterministic */
     const float* u1;               /* randomized: (n_rays, n_fine) uniforms, helper.py:587 */
+    int precision;                 /* NeoPrecision: NEO_PREC_FP32 = fused fp32 CUDA-core field kernel (tight parity), NEO_PREC_TC = NeRFMLP layer by layer
+                                      on tcgen05 (csrc/gemm_tc.cu), fp16 weights / activations */
 } NeoVanillaCfg;
 typedef struct {
     float* comp_rgb[2];  /* (n_rays,3)   model.py:214 returns (comp_rgb, acc, depth) per level */

@@ -52,7 +52,7 @@ class NeoVanillaMLPParams(C.Structure):
 
 class NeoVanillaCfg(C.Structure):
     _fields_ = [("n_coarse", C.c_int), ("n_fine", C.c_int), ("white_bkgd", C.c_int), ("near_plane", C.c_float), ("far_plane", C.c_float),
-                ("u0", C.c_void_p), ("u1", C.c_void_p)]
+                ("u0", C.c_void_p), ("u1", C.c_void_p), ("precision", C.c_int)]
 
 
 VANILLA_OUT_FIELDS = ("comp_rgb", "acc", "depth", "t", "sigma", "rgb_s", "weights")

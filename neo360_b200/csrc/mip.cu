@@ -385,6 +385,11 @@ __global__ void rowdot_f16_kernel(const __half* __restrict__ H, long long ld, in
 }
 
 }  // namespace mip
+int launch_rowdot_f16(const void* H, long long ld, int K, const float* W, const float* b, int N, long long M, float* out, cudaStream_t s) {
+    mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>((const __half*)H, ld, K, W, b, N, M, out);
+    NEO_LAUNCH_CHECK("rowdot_f16_kernel");
+    return NEO_OK;
+}
 // csrc/gemm_tc.cu
 int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* C, long long ldc, long long M, int N, int K,
              int relu, cudaStream_t s);

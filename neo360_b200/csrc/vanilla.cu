@@ -3,12 +3,16 @@
 // models/vanilla_nerf/helper.py:415-442 (sampling), 445-449 (pos-enc), 521-559 (compositing), 567-616 (inverse CDF).
 // Sampling marches along `viewdirs`, compositing scales by |rays_d| (quirk Q15); depth gets nan_to_num(inf) (quirk Q10).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 struct NeoVanilla {
     struct Mlp {
         const float* wt[8];   // transposed (in,out)
         const float* b[8];
         const float *wbt, *bb, *wsig, *bsig, *wv0t, *bv0, *wrgb, *brgb;
+        // tensor-core path (NEO_PREC_TC): nn.Linear layout (out, in padded to a multiple of 64) in fp16
+        const void* w16[8];   // (256, 64) | (256,256) x4 | (256, 256+64) | (256,256) x2
+        const void *wb16, *wv016;   // (256,256), (128, 256+64)
     } mlp[2];
     std::vector<void*> allocations;
     size_t bytes;
@@ -160,7 +164,62 @@ __global__ void __launch_bounds__(kThreads) field_kernel(NeoVanilla::Mlp m, cons
     }
 }
 
+// ---- tensor-core path: positional encodings as fp16 rows (63 -> 64, 27 -> 64 zero padded), activations of the heads ----
+__global__ void enc16_kernel(const float* __restrict__ rays_o, const float* __restrict__ viewdirs, const float* __restrict__ tvals, long long M, int N,
+                             __half* __restrict__ X16, long long ldx, __half* __restrict__ D16, long long ldd) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= M * 128) return;
+    const long long m = gid >> 7;
+    const int c = (int)(gid & 127);
+    const int b = (int)(m / N);
+    if (c < 64) {
+        float val = 0.f;
+        if (c < kEnc) {
+            const float t = tvals[m];
+            if (c < 3) val = add_(rays_o[3 * b + c], mul_(t, viewdirs[3 * b + c]));
+            else {
+                int q = c - 3;
+                const bool shifted = q >= 30;
+                if (shifted) q -= 30;
+                const float x = add_(rays_o[3 * b + q % 3], mul_(t, viewdirs[3 * b + q % 3]));
+                const float xb = mul_(x, (float)(1 << (q / 3)));
+                val = sinf(shifted ? add_(xb, 1.57079637f) : xb);
+            }
+        }
+        X16[m * ldx + c] = __float2half_rn(val);
+    } else {
+        const int cc = c - 64;
+        float val = 0.f;
+        if (cc < 27) {
+            const float* d = viewdirs + 3 * b;
+            if (cc < 3) val = d[cc];
+            else {
+                int q = cc - 3;
+                const bool shifted = q >= 12;
+                if (shifted) q -= 12;
+                const float xb = mul_(d[q % 3], (float)(1 << (q / 3)));
+                val = sinf(shifted ? add_(xb, 1.57079637f) : xb);
+            }
+        }
+        D16[m * ldd + cc] = __float2half_rn(val);
+    }
+}
+__global__ void head_act_kernel(const float* __restrict__ raw_sigma, const float* __restrict__ raw_rgb, long long M, float* __restrict__ sigma,
+                                float* __restrict__ rgb) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * 4) return;
+    const long long m = i >> 2;
+    const int c = (int)(i & 3);
+    if (c == 3) { const float xs = raw_sigma[m] - 1.0f; sigma[m] = xs > 20.f ? xs : log1pf(expf(xs)); }
+    else rgb[m * 3 + c] = (1.f / (1.f + expf(-raw_rgb[m * 3 + c]))) * 1.002f - 0.001f;
+}
+
 }  // namespace van
+// csrc/gemm_tc.cu, csrc/mip.cu
+int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* C, long long ldc, long long M, int N, int K,
+             int relu, cudaStream_t s);
+int f32_to_f16_pad(const float* in, long long rows, int cols_in, long long ld_in, void* out, int cols_out, long long ld_out, cudaStream_t s);
+int launch_rowdot_f16(const void* H, long long ld, int K, const float* W, const float* b, int N, long long M, float* out, cudaStream_t s);
 }  // namespace neo
 
 using namespace neo;
@@ -172,14 +231,23 @@ __global__ void transpose2(const float* __restrict__ w, float* __restrict__ wt, 
     wt[(size_t)(idx % in_f) * out_f + idx / in_f] = w[idx];
 }
 struct Carver2 { float* base; size_t used; float* take(size_t n) { n = (n + 63) & ~size_t(63); float* p = base ? base + used : nullptr; used += n; return p; } };
-struct WSV { float *t0, *w0, *t1, *w1, *sig, *rgb; };
-size_t carve2(Carver2& c, int n, int N0, int N1, WSV& w) {
+struct WSV { float *t0, *w0, *t1, *w1, *sig, *rgb; void *A16[2], *B16, *V16; float *rawd, *rawc; };
+constexpr int kLdA = 256 + 64, kLdB = 256 + 64;      // activation rows: [h (256) | padded encoding (64)], [bottleneck (256) | padded direction encoding (64)]
+size_t carve2(Carver2& c, int n, int N0, int N1, WSV& w, int precision) {
     w.t0 = c.take((size_t)n * N0); w.w0 = c.take((size_t)n * N0); w.t1 = c.take((size_t)n * N1); w.w1 = c.take((size_t)n * N1);
     w.sig = c.take((size_t)n * N1); w.rgb = c.take((size_t)n * N1 * 3);
+    if (precision == NEO_PREC_TC) {
+        const size_t M = (size_t)n * N1;
+        for (int i = 0; i < 2; ++i) w.A16[i] = c.take((M * kLdA + 1) / 2);
+        w.B16 = c.take((M * kLdB + 1) / 2);
+        w.V16 = c.take((M * 128 + 1) / 2);
+        w.rawd = c.take(M); w.rawc = c.take(M * 3);
+    }
     return c.used * sizeof(float);
 }
 int check(const NeoVanillaCfg* c) {
     if (!c || c->n_coarse < 3 || c->n_fine < 1 || c->n_coarse > 4096 || c->n_fine > 4096) { set_error("vanilla: bad sample counts"); return NEO_ERR_INVALID; }
+    if (c->precision != NEO_PREC_FP32 && c->precision != NEO_PREC_TC) { set_error("vanilla: bad precision %d", c->precision); return NEO_ERR_INVALID; }
     return NEO_OK;
 }
 }  // namespace
@@ -218,6 +286,32 @@ extern "C" int neo_vanilla_create(const NeoVanillaMLPParams mlps[2], NeoVanilla*
         if ((rc = dup(p.bv0, 128, &m.bv0, 0, 0))) return fail(rc);
         if ((rc = dup(p.wrgb, 3 * 128, &m.wrgb, 0, 0))) return fail(rc);
         if ((rc = dup(p.brgb, 3, &m.brgb, 0, 0))) return fail(rc);
+        // fp16 images for the tensor-core path: K padded to a multiple of 64; the skip layer's [h | inputs] columns land at [0,256) | [256,319)
+        auto pack16 = [&](const float* src, int rows, int c0, int ncols, int ld_in, void* dst, int off, int pad_cols, int ld_out) -> int {
+            return f32_to_f16_pad(src + c0, rows, ncols, ld_in, (__half*)dst + off, pad_cols, ld_out, s);
+        };
+        auto alloc16 = [&](size_t halves, const void** dst) -> int {
+            void* q = nullptr;
+            cudaError_t e = cudaMalloc(&q, halves * 2);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(vanilla fp16)");
+            v->allocations.push_back(q);
+            v->bytes += halves * 2;
+            *dst = q;
+            return NEO_OK;
+        };
+        for (int l = 0; l < 8; ++l) {
+            const int in_f = l == 0 ? 63 : (l == 5 ? 319 : 256), kp = l == 0 ? 64 : (l == 5 ? 320 : 256);
+            if ((rc = alloc16((size_t)256 * kp, &m.w16[l]))) return fail(rc);
+            if (l == 5) {
+                if ((rc = pack16(p.w[l], 256, 0, 256, in_f, (void*)m.w16[l], 0, 256, kp))) return fail(rc);
+                if ((rc = pack16(p.w[l], 256, 256, 63, in_f, (void*)m.w16[l], 256, 64, kp))) return fail(rc);
+            } else if ((rc = pack16(p.w[l], 256, 0, in_f, in_f, (void*)m.w16[l], 0, kp, kp))) return fail(rc);
+        }
+        if ((rc = alloc16((size_t)256 * 256, &m.wb16))) return fail(rc);
+        if ((rc = pack16(p.wb, 256, 0, 256, 256, (void*)m.wb16, 0, 256, 256))) return fail(rc);
+        if ((rc = alloc16((size_t)128 * 320, &m.wv016))) return fail(rc);
+        if ((rc = pack16(p.wv0, 128, 0, 256, 283, (void*)m.wv016, 0, 256, 320))) return fail(rc);
+        if ((rc = pack16(p.wv0, 128, 256, 27, 283, (void*)m.wv016, 256, 64, 320))) return fail(rc);
     }
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(cuda_fail(e, "neo_vanilla_create sync"));
@@ -235,7 +329,7 @@ extern "C" size_t neo_vanilla_workspace_bytes(int n_rays, const NeoVanillaCfg* c
     if (n_rays <= 0 || check(cfg)) return 0;
     Carver2 c{nullptr, 0};
     WSV w;
-    return carve2(c, n_rays, cfg->n_coarse + 1, cfg->n_coarse + 1 + cfg->n_fine, w);
+    return carve2(c, n_rays, cfg->n_coarse + 1, cfg->n_coarse + 1 + cfg->n_fine, w, cfg->precision);
 }
 
 extern "C" int neo_vanilla_render_fwd(const NeoVanilla* v, const NeoRays* rays, const NeoVanillaCfg* cfg, NeoVanillaOut* out,
@@ -248,7 +342,7 @@ extern "C" int neo_vanilla_render_fwd(const NeoVanilla* v, const NeoRays* rays, 
     const int n = rays->n_rays, N0 = cfg->n_coarse + 1, N1 = N0 + cfg->n_fine;
     Carver2 c{reinterpret_cast<float*>(workspace), 0};
     WSV w;
-    size_t need = carve2(c, n, N0, N1, w);
+    size_t need = carve2(c, n, N0, N1, w, cfg->precision);
     if (!workspace || workspace_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes); return NEO_ERR_WORKSPACE; }
     for (int lvl = 0; lvl < 2; ++lvl) {
         const int N = lvl ? N1 : N0;
@@ -264,9 +358,31 @@ extern "C" int neo_vanilla_render_fwd(const NeoVanilla* v, const NeoRays* rays, 
             if ((rc = launch_resample(rays->rays_o, rays->viewdirs, nullptr, w.t0, w.w0, n, N0, cfg->n_fine, 1, 0.f, cfg->u1, t, nullptr, nullptr, s))) return rc;
         }
         long long total = (long long)n * N;
-        van::field_kernel<<<(unsigned)((total + van::kP - 1) / van::kP), van::kThreads, 0, s>>>(v->mlp[lvl], rays->rays_o, rays->viewdirs, t, n, N,
-                                                                                                  w.rgb, w.sig);
-        NEO_LAUNCH_CHECK("vanilla field_kernel");
+        if (cfg->precision == NEO_PREC_TC) {
+            // NeRFMLP (models/vanilla_nerf/model.py:44-125) layer by layer on tcgen05 (csrc/gemm_tc.cu), fp16 activations; the skip concatenation
+            // by keeping h4 and the encoding in ONE buffer (layer 5 is a single K = 320 GEMM)
+            const NeoVanilla::Mlp& m = v->mlp[lvl];
+            __half* buf[2] = {(__half*)w.A16[0], (__half*)w.A16[1]};
+            __half* B = (__half*)w.B16;
+            van::enc16_kernel<<<(unsigned)((total * 128 + 255) / 256), 256, 0, s>>>(rays->rays_o, rays->viewdirs, t, total, N, buf[0] + 256, kLdA, B + 256, kLdB);
+            NEO_LAUNCH_CHECK("vanilla enc16_kernel");
+            if ((rc = gemm_f16(buf[0] + 256, kLdA, m.w16[0], 64, m.b[0], buf[0], kLdA, total, 256, 64, 1, s))) return rc;
+            for (int l = 1; l < 8; ++l) {
+                const int K = l == 5 ? 320 : 256;
+                if ((rc = gemm_f16(buf[(l - 1) & 1], kLdA, m.w16[l], K, m.b[l], buf[l & 1], kLdA, total, 256, K, 1, s))) return rc;
+            }
+            const __half* h = buf[1];
+            if ((rc = launch_rowdot_f16(h, kLdA, 256, m.wsig, m.bsig, 1, total, w.rawd, s))) return rc;
+            if ((rc = gemm_f16(h, kLdA, m.wb16, 256, m.bb, B, kLdB, total, 256, 256, 0, s))) return rc;
+            if ((rc = gemm_f16(B, kLdB, m.wv016, 320, m.bv0, w.V16, 128, total, 128, 320, 1, s))) return rc;
+            if ((rc = launch_rowdot_f16(w.V16, 128, 128, m.wrgb, m.brgb, 3, total, w.rawc, s))) return rc;
+            van::head_act_kernel<<<(unsigned)((total * 4 + 255) / 256), 256, 0, s>>>(w.rawd, w.rawc, total, w.sig, w.rgb);
+            NEO_LAUNCH_CHECK("vanilla head_act_kernel");
+        } else {
+            van::field_kernel<<<(unsigned)((total + van::kP - 1) / van::kP), van::kThreads, 0, s>>>(v->mlp[lvl], rays->rays_o, rays->viewdirs, t, n, N,
+                                                                                                      w.rgb, w.sig);
+            NEO_LAUNCH_CHECK("vanilla field_kernel");
+        }
         // mode 2: ascending t, last interval 1e10, scaled by |rays_d|, depth nan_to_num(inf)
         if ((rc = launch_composite(w.rgb, w.sig, t, rays->rays_d, nullptr, n, N, cfg->white_bkgd, 2, out->comp_rgb[lvl], out->acc[lvl], wt, nullptr,
                                    out->depth[lvl], s))) return rc;

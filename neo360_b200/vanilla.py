@@ -102,6 +102,7 @@ class NeRF(nn.Module):
         cfg = L.NeoVanillaCfg()
         cfg.n_coarse, cfg.n_fine, cfg.white_bkgd = nc, nf, int(bool(white_bkgd))
         cfg.near_plane, cfg.far_plane = float(near), float(far)
+        cfg.precision = {"fp32": L.NEO_PREC_FP32, "tc": L.NEO_PREC_TC}[getattr(self, "precision", "fp32")]
         keep = []
         if randomized:
             u = rays.get("_uniforms") or [torch.rand((n, nc + 1), device=dev), torch.rand((n, nf), device=dev)]   # helper.py:438, 587

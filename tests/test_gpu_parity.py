@@ -385,6 +385,32 @@ def test_vanilla_nerf_vs_reference_vectors(cuda, tag):
                 assert float(diff.max()) < 5e-3 and float((diff > 2e-4).double().mean()) <= 0.01, (lvl, n_, float(diff.max()))
 
 
+@pytest.mark.parametrize("tag", ["v_tiny", "v_cfg1"])
+def test_vanilla_nerf_tc_vs_reference_vectors(cuda, tag):
+    """Vanilla NeRF with the 8 x 256 MLP layer by layer on tcgen05 (NEO_PREC_TC, fp16 weights / activations) against outputs of the
+    UNMODIFIED reference module (v_cfg1 = BASELINE configs[0]).  Stated: L-inf <= 3e-2 on rgb / acc, PSNR >= 40 dB; coarse sample
+    positions bit-exact."""
+    import os
+    from neo360_b200.vanilla import NeRF
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vanilla_reference_vectors.npz"))
+    W, H, B, nc, nf, seed = [int(x) for x in g[f"{tag}_cfg"]]
+    net = NeRF(num_coarse_samples=nc, num_fine_samples=nf).eval()
+    net.precision = "tc"
+    net.load_state_dict(synth.make_vanilla_params(seed))
+    net = net.to(cuda)
+    rays = {k: T(g[f"{tag}_{k}"]).to(cuda) for k in ("rays_o", "rays_d", "viewdirs")}
+    with torch.no_grad():
+        ev = net(rays, False, True, 0.2, 3.0, debug=True)
+    torch.cuda.synchronize()
+    if tag == "v_tiny":
+        assert md(net.last_debug["t"][0], T(g["v_tiny_aux0_t"])) == 0
+    for lvl in range(2):
+        e_rgb, e_acc = md(ev[lvl][0], T(g[f"{tag}_eval{lvl}_rgb"])), md(ev[lvl][1], T(g[f"{tag}_eval{lvl}_acc"]))
+        ps = orc.psnr(ev[lvl][0].cpu(), T(g[f"{tag}_eval{lvl}_rgb"]))
+        print(f"vanilla tc [{tag}] level {lvl}: L-inf rgb {e_rgb:.2e} acc {e_acc:.2e} PSNR {ps:.1f} dB")
+        assert e_rgb < 3e-2 and e_acc < 3e-2 and ps > 40.0, (lvl, e_rgb, e_acc, ps)
+
+
 def test_tc_blocked_frame_order_is_pure_scheduling(cuda):
     """NEO_PREC_TC with NeoRays.ray_order (8x4 pixel blocks) against the identity order.  The ray order decides which 64 points
     share a job and therefore how a point's texel windows are grouped, i.e. the order of its fp32 accumulation on the tensor pipe:
