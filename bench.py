@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="debug: skip the CPU oracle leg (and with it the parity block)")
     ap.add_argument("--no-extras", action="store_true", help="debug: skip the eager-GPU reference leg and the call-pattern variants")
-    ap.add_argument("--mode", default="frames", choices=["frames", "strong", "turntable", "train", "mip360", "vanilla"],
+    ap.add_argument("--mode", default="frames", choices=["frames", "strong", "turntable", "train", "mip360", "vanilla", "encoder"],
                     help="frames: BASELINE configs[1], one frame per rank (the headline, default); strong: ONE 640x480 frame split over the ranks "
                          "+ NCCL all-gather of the pixels (models/interface.py:30-50); turntable: BASELINE configs[4], views sharded first; "
                          "train: BASELINE configs[3], 4096-ray batches with an NCCL gradient all-reduce; mip360: BASELINE configs[2], "

@@ -213,6 +213,35 @@ def run(args, rank, world, local, dev, dist, pk):
                     e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 12},
                     clocks=sampler.result() if sampler else None)
 
+    if args.mode == "encoder":
+        # GridEncoder.forward per scene (3 source views at 640x480): ResNet trunk + dense part + conv stacks; the dense part
+        # (64^3 x 3 grid lookup, DepthPillarEncoder, three pillar aggregators: 2.7 TFLOP) timed as hand-written CUDA vs framework ops
+        from neo360_b200.encoder import GridEncoder
+        from neo360_b200 import synth
+        torch.manual_seed(0)
+        enc = GridEncoder().eval().to(dev)
+        sc = synth.make_scene((64, 48), B.NV, (12, 16), 0)
+        poses, focal, c = sc["src_poses"].to(dev), torch.full((B.NV,), 0.8 * B.IMG_W, device=dev), torch.tensor([[B.IMG_W / 2.0, B.IMG_H / 2.0]] * B.NV, device=dev)
+        imgs = torch.rand(B.NV, 3, B.IMG_H, B.IMG_W, device=dev) * 2 - 1
+        res = {}
+        with torch.no_grad():
+            lat = enc.spatial_encoder(imgs)
+            for name, fn in (("dense_cuda_tcgen05", lambda: enc.dense_cuda(lat, poses, focal, c, B.IMG_W, B.IMG_H)),
+                             ("dense_framework_fp32", lambda: enc.dense_torch(lat, poses, focal, c, B.IMG_W, B.IMG_H)),
+                             ("whole_forward", lambda: enc(imgs, poses, focal, c))):
+                res[name] = _timed(lambda s: fn(), args.steps, args.warmup, dev, dist) / args.steps
+        rows = B.NV * 64 ** 3
+        flop = 2.0 * rows * (518 * 512 + 2 * 512 * 512 + 3 * (513 * 512 + 512))
+        return dict(base, metric="GridEncoder scenes/sec (3 source views, 640x480)", unit="scenes/s", value=1e3 / res["whole_forward"],
+                    ms_per_step=res["whole_forward"], scaling="weak", dtype="f16 operands, f32 accumulate (tcgen05) for the dense part",
+                    config={"workload": "GridEncoder.forward: ResNet-34 trunk (framework) + dense part (hand-written CUDA) + 3 conv stacks (framework)",
+                            "rows": rows, "parallelism": "one scene per rank"},
+                    dense_part_ms=res, roofline={"bound": "tensor", "achieved": flop / (res["dense_cuda_tcgen05"] * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
+                                                 "unit": "TFLOP/s", "frac": flop / (res["dense_cuda_tcgen05"] * 1e-3) / 1e12 / pk["bf16_tflops"],
+                                                 "traffic": None, "peak_source": pk["src"],
+                                                 "flops": f"{flop / 1e12:.2f} TFLOP of dense layers per scene over the dense part's time (gather, softmax sums included)"},
+                    speedup_dense_vs_framework_fp32=res["dense_framework_fp32"] / res["dense_cuda_tcgen05"])
+
     if args.mode == "train":
         from neo360_b200 import training
         return training.bench_train(args, rank, world, local, dev, dist, pk, base, sampler, _timed)

@@ -265,6 +265,24 @@ int neo_mip_render_fwd(const NeoMipMLPParams mlps[3], const float* rays_o, const
                        const float* radii, int n_rays, const NeoMipCfg* cfg, NeoMipOut* out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- tri-plane builder, dense part: models/neo360/encoder_tp_fusion_conv.py:472-597 between the ResNet feature
+ * extractor and the floor-plan conv stacks (both stay in the host framework).  64^3 world grid x nv views: latent lookup, DepthPillarEncoder
+ * 518->512->512->512, three pillar aggregators (513->512->1, softmax along one grid axis), softmax-weighted pillar sums.  Every dense layer
+ * runs on tcgen05 (csrc/gemm_tc.cu, fp16 weights / activations, fp32 accumulation).  nn.Linear layout (out,in) fp32 device pointers. ---- */
+typedef struct {
+    const float* fc_w[3];   /* depth_fc.common_branch.0 (512,518), depth_fc.common_branch.2 (512,512), depth_fc.depth_encoder (512,512) */
+    const float* fc_b[3];
+    const float *agg_xz_w0, *agg_xz_b0, *agg_xz_w1, *agg_xz_b1;   /* pillar_aggregator_xz.{0,2}: (512,513), (512), (1,512), (1) */
+    const float *agg_yz_w0, *agg_yz_b0, *agg_yz_w1, *agg_yz_b1;
+    const float *agg_xy_w0, *agg_xy_b0, *agg_xy_w1, *agg_xy_b1;
+} NeoGridEncoderParams;
+size_t neo_grid_encoder_workspace_bytes(int nv, int lat_h, int lat_w);
+/* latent (nv,512,lat_h,lat_w) NCHW = SpatialEncoder output; src_poses (nv,4,4) camera-to-world; focal / (cx,cy) = src_focal[0] / src_c[0].
+ * Outputs: the three pillar-aggregated floor plans (nv,512,64,64) NCHW that feed floorplan_convnet_{xz,xy,yz}. */
+int neo_grid_encoder_dense(const NeoGridEncoderParams* params, const float* latent, int nv, int lat_h, int lat_w, int img_w, int img_h,
+                           const float* src_poses, float focal, float cx, float cy, float* floor_xz, float* floor_xy, float* floor_yz,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* bench support: CUDA events around every field-kernel launch on the launching stream + launch accounting.
  * neo_profile(1) resets and enables, neo_profile(0) resets and disables; neo_profile_read synchronises. */
 int neo_profile(int enable);

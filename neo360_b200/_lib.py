@@ -79,6 +79,11 @@ class NeoMipOut(C.Structure):
     _fields_ = [(n, C.c_void_p * 3) for n in MIP_OUT_FIELDS]
 
 
+class NeoGridEncoderParams(C.Structure):
+    _fields_ = [("fc_w", C.c_void_p * 3), ("fc_b", C.c_void_p * 3)] + \
+               [(f"agg_{pl}_{n}", C.c_void_p) for pl in ("xz", "yz", "xy") for n in ("w0", "b0", "w1", "b1")]
+
+
 # every symbol include/neo360_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "neo_scene_create": (C.c_int, [C.POINTER(NeoSceneDesc), C.POINTER(NeoMLPParams), C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
@@ -106,6 +111,9 @@ SYMBOLS = {
     "neo_mip_workspace_bytes": (C.c_size_t, [C.c_int, C.POINTER(NeoMipCfg), C.c_int]),
     "neo_mip_render_fwd": (C.c_int, [C.POINTER(NeoMipMLPParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(NeoMipCfg),
                                      C.POINTER(NeoMipOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "neo_grid_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "neo_grid_encoder_dense": (C.c_int, [C.POINTER(NeoGridEncoderParams), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "neo_profile": (C.c_int, [C.c_int]),
     "neo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "neo_tc_selftest": (C.c_int, [C.c_void_p] * 8),
