@@ -109,6 +109,7 @@ class MipNeRF360(nn.Module):
                 getattr(out, k)[l] = t.data_ptr()
             ren.append({"rgb": T["rgb"]})
             hist.append({"density": T["density"], "rgb": T["rgb_s"], "sdist": T["sdist"], "weights": T["weights"]})
-        L.check(lib.neo_mip_render_fwd(arr, L.ptr(o), L.ptr(d), L.ptr(vd), L.ptr(radii), n, C.byref(cfg), C.byref(out), self._ws.data_ptr(),
-                                       self._ws.numel(), torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(dev):
+            L.check(lib.neo_mip_render_fwd(arr, L.ptr(o), L.ptr(d), L.ptr(vd), L.ptr(radii), n, C.byref(cfg), C.byref(out), self._ws.data_ptr(),
+                                           self._ws.numel(), torch.cuda.current_stream().cuda_stream))
         return ren, hist

@@ -18,6 +18,20 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _on:
+    """Device guard: kernels and the stream handed to the library belong to the device of the call's tensors, not to whatever device
+    happens to be current in the process."""
+
+    def __init__(self, t):
+        self.g = torch.cuda.device(t.device)
+
+    def __enter__(self):
+        self.g.__enter__()
+
+    def __exit__(self, *e):
+        return self.g.__exit__(*e)
+
+
 def _f32(t):
     if not t.is_cuda:
         raise RuntimeError("neo360_b200 ops run on CUDA tensors only (no CPU fallback)")
@@ -31,7 +45,8 @@ def get_rays(H, W, focal, c2w, output_radii=True):
     n = H * W
     o = torch.empty(n, 3, device=m.device); vd = torch.empty_like(o); rd = torch.empty_like(o)
     rad = torch.empty(n, device=m.device) if output_radii else None
-    L.check(lib.neo_get_rays(H, W, float(focal), L.ptr(m), L.ptr(o), L.ptr(vd), L.ptr(rd), L.ptr(rad), _stream()))
+    with _on(m):
+        L.check(lib.neo_get_rays(H, W, float(focal), L.ptr(m), L.ptr(o), L.ptr(vd), L.ptr(rd), L.ptr(rad), _stream()))
     return (o, vd, rd, rad) if output_radii else (o, vd, rd)
 
 
@@ -41,7 +56,8 @@ def intersect_sphere(rays_o, rays_d):
     n = o.shape[0]
     far = torch.empty(n, 1, device=o.device)
     err = torch.zeros(1, dtype=torch.int32, device=o.device)
-    L.check(lib.neo_intersect_sphere(L.ptr(o), L.ptr(d), n, L.ptr(far), L.ptr(err), _stream()))
+    with _on(o):
+        L.check(lib.neo_intersect_sphere(L.ptr(o), L.ptr(d), n, L.ptr(far), L.ptr(err), _stream()))
     if int(err.item()):   # the reference asserts synchronously here (helper.py:271)
         raise AssertionError("1.0 - p_norm_sq should be greater than 0")
     return far
@@ -61,13 +77,15 @@ def sample_along_rays(rays_o, rays_d, num_samples, near, far, randomized, lindis
     t = torch.empty(n, N, device=o.device)
     if in_sphere:
         pts = torch.empty(n, N, 3, device=o.device)
-        L.check(lib.neo_sample_along_rays(L.ptr(o), L.ptr(d), L.ptr(fr), n, num_samples, 1, float(far_uncontracted),
-                                          L.ptr(u), L.ptr(t), L.ptr(pts), None, _stream()))
+        with _on(o):
+            L.check(lib.neo_sample_along_rays(L.ptr(o), L.ptr(d), L.ptr(fr), n, num_samples, 1, float(far_uncontracted),
+                                              L.ptr(u), L.ptr(t), L.ptr(pts), None, _stream()))
         return t, pts
     pts = torch.empty(n, N, 4, device=o.device)
     lin = torch.empty(n, N, 3, device=o.device)
-    L.check(lib.neo_sample_along_rays(L.ptr(o), L.ptr(d), L.ptr(fr), n, num_samples, 0, float(far_uncontracted),
-                                      L.ptr(u), L.ptr(t), L.ptr(pts), L.ptr(lin), _stream()))
+    with _on(o):
+        L.check(lib.neo_sample_along_rays(L.ptr(o), L.ptr(d), L.ptr(fr), n, num_samples, 0, float(far_uncontracted),
+                                          L.ptr(u), L.ptr(t), L.ptr(pts), L.ptr(lin), _stream()))
     return t, pts, lin
 
 
@@ -86,13 +104,15 @@ def sample_pdf(t_vals, weights, origins, directions, num_samples, randomized, in
     t = torch.empty(n, N1, device=o.device)
     if in_sphere:
         pts = torch.empty(n, N1, 3, device=o.device)
-        L.check(lib.neo_sample_pdf(L.ptr(o), L.ptr(d), L.ptr(fr), L.ptr(t_old), L.ptr(w), n, n_old, num_samples, 1,
-                                   float(far_uncontracted), L.ptr(u), L.ptr(t), L.ptr(pts), None, _stream()))
+        with _on(o):
+            L.check(lib.neo_sample_pdf(L.ptr(o), L.ptr(d), L.ptr(fr), L.ptr(t_old), L.ptr(w), n, n_old, num_samples, 1,
+                                       float(far_uncontracted), L.ptr(u), L.ptr(t), L.ptr(pts), None, _stream()))
         return t, pts
     pts = torch.empty(n, N1, 4, device=o.device)
     lin = torch.empty(n, N1, 3, device=o.device)
-    L.check(lib.neo_sample_pdf(L.ptr(o), L.ptr(d), L.ptr(fr), L.ptr(t_old), L.ptr(w), n, n_old, num_samples, 0,
-                               float(far_uncontracted), L.ptr(u), L.ptr(t), L.ptr(pts), L.ptr(lin), _stream()))
+    with _on(o):
+        L.check(lib.neo_sample_pdf(L.ptr(o), L.ptr(d), L.ptr(fr), L.ptr(t_old), L.ptr(w), n, n_old, num_samples, 0,
+                                   float(far_uncontracted), L.ptr(u), L.ptr(t), L.ptr(pts), L.ptr(lin), _stream()))
     return t, pts, lin
 
 
@@ -104,9 +124,10 @@ def volumetric_rendering(rgb, density, t_vals, dirs, white_bkgd, in_sphere, t_fa
     comp = torch.empty(n, 3, device=t.device); acc = torch.empty(n, device=t.device)
     w = torch.empty(n, N, device=t.device); depth = torch.empty(n, device=t.device)
     lam = torch.empty(n, 1, device=t.device) if in_sphere else None
-    L.check(lib.neo_volumetric_rendering(L.ptr(rgb), L.ptr(sig), L.ptr(t), L.ptr(d), L.ptr(far), n, N, int(bool(white_bkgd)),
-                                         int(bool(in_sphere)), L.ptr(comp), L.ptr(acc), L.ptr(w), L.ptr(lam), L.ptr(depth),
-                                         _stream()))
+    with _on(t):
+        L.check(lib.neo_volumetric_rendering(L.ptr(rgb), L.ptr(sig), L.ptr(t), L.ptr(d), L.ptr(far), n, N, int(bool(white_bkgd)),
+                                             int(bool(in_sphere)), L.ptr(comp), L.ptr(acc), L.ptr(w), L.ptr(lam), L.ptr(depth),
+                                             _stream()))
     if out_depth is not None:
         return comp, acc, w, lam, depth
     return comp, acc, w, lam

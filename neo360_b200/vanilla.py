@@ -72,7 +72,8 @@ class NeRF(nn.Module):
             keep = []
             arr = (L.NeoVanillaMLPParams * 2)(self.coarse_mlp.to(dev).c_params(keep), self.fine_mlp.to(dev).c_params(keep))
             h = C.c_void_p()
-            L.check(lib.neo_vanilla_create(arr, C.byref(h), torch.cuda.current_stream().cuda_stream))
+            with torch.cuda.device(dev):
+                L.check(lib.neo_vanilla_create(arr, C.byref(h), torch.cuda.current_stream().cuda_stream))
             self._handle, self._key = h, tuple((p.data_ptr(), p._version) for p in self.parameters())
         return self._handle
 
@@ -127,8 +128,9 @@ class NeRF(nn.Module):
                 t = torch.empty(*shp, device=dev)
                 T[k].append(t)
                 getattr(out, k)[lvl] = t.data_ptr()
-        L.check(lib.neo_vanilla_render_fwd(h, C.byref(r), C.byref(cfg), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
-                                           torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(dev):
+            L.check(lib.neo_vanilla_render_fwd(h, C.byref(r), C.byref(cfg), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
+                                               torch.cuda.current_stream().cuda_stream))
         if debug:
             self.last_debug = T
         return [(T["comp_rgb"][lvl], T["acc"][lvl], T["depth"][lvl]) for lvl in range(2)]
