@@ -153,6 +153,13 @@ int neo_check_async(const NeoScene* scene, void* stream);
 /* datasets/ray_utils.py:84-104 + 133-176: pixel grid + c2w (3,4 row-major, device) -> rays. */
 int neo_get_rays(int H, int W, float focal, const float* c2w, float* rays_o, float* viewdirs, float* rays_d,
                  float* radii, void* stream);
+/* datasets/nerds360_ae.py:730-748 (train __getitem__): `n` sampled pixels of `n_views` target views.  pix_inds (n) int64 index the
+ * flattened (n_views, H, W) stack exactly as the reference's `torch.randint(0, T*H*W)` does; c2w (n_views,3,4); images
+ * (n_views,H,W,3) fp32 or NULL.  Outputs (n,3)/(n) as neo_get_rays, target (n,3) = images[pix]; any output may be NULL.  Each ray is
+ * bit-identical to the same pixel of neo_get_rays.  Out-of-range indices raise *err_flag (device int) = NEO_ERR_INVALID. */
+int neo_sample_rays(int n, const long long* pix_inds, int n_views, int H, int W, float focal, const float* c2w,
+                    const float* images, float* rays_o, float* viewdirs, float* rays_d, float* radii, float* target,
+                    int* err_flag, void* stream);
 /* models/neo360/helper.py:253-273 */
 int neo_intersect_sphere(const float* rays_o, const float* rays_d, int n_rays, float* far, int* err_flag,
                          void* stream);

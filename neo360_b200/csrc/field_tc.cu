@@ -403,48 +403,31 @@ __host__ __device__ inline uint32_t sw128_off(int row, int k, int rows) {
 // ------------------------------------------------------------------------------------------------
 // per-scene preparation kernels
 // ------------------------------------------------------------------------------------------------
-// P[((v*4 + half*2 + n/64)*HW + p)*64 + n%64] = sum_c W[n*ldw + col0 + c] * in[(v*C + c)*HW + p]     (fp32 math, fp16 store)
-// i.e. projected channel n' = half*128 + n of texel p lives in channel group n'/64: the TMA box of the field kernel stages
-// one 128-byte row per (texel, group).
-__global__ void __launch_bounds__(256) preproject_kernel(const float* __restrict__ in, int C, int HW,
-                                                         const float* __restrict__ W, int ldw, int col0, int half_sel,
-                                                         __half* __restrict__ out) {
-    __shared__ float As[16][64 + 4];   // [k][pixel]
-    __shared__ float Bs[16][64 + 4];   // [k][n]
-    const int v = blockIdx.z, p0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;      // tx -> n, ty -> pixel
-    float acc[4][4] = {};
-    const float* inv = in + (size_t)v * C * HW;
-    for (int k0 = 0; k0 < C; k0 += 16) {
-        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            int kk = e / 64, pp = e % 64;
-            int p = p0 + pp;
-            As[kk][pp] = (p < HW) ? inv[(size_t)(k0 + kk) * HW + p] : 0.f;
-        }
-        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            int nn = e / 16, kk = e % 16;
-            Bs[kk][nn] = W[(size_t)(n0 + nn) * ldw + col0 + k0 + kk];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
+// Per scene and MLP the latent columns of layers 0 and 3 are applied to the raw feature maps once (linearity of the lookups):
+// P[(v*4 + n'/64)][p][n'%64] = sum_c Wsel[n'][c] * F[v][c][p],  n' in [0,256) = [P0 | P3] -- a plain contraction, run on tcgen05 by
+// gemm_f16 (csrc/gemm_tc.cu) from the two operands prepared below.
+// (n, C, HW) fp32 -> (n, HW, C) fp16: the A operand (pixels x channels, K-major) of the tensor-core pre-projection
+__global__ void nchw_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const float* src = in + (size_t)n * C * HW;
+    __half* dst = out + (size_t)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) tile[i][threadIdx.x] = src[(size_t)c * HW + p];
     }
-    for (int i = 0; i < 4; ++i) {
-        int p = p0 + ty * 4 + i;
-        if (p >= HW) continue;
-        __half* o = out + (((size_t)v * 4 + half_sel * 2 + (n0 >> 6)) * HW + p) * 64 + tx * 4;
-        o[0] = __float2half_rn(acc[i][0]); o[1] = __float2half_rn(acc[i][1]);
-        o[2] = __float2half_rn(acc[i][2]); o[3] = __float2half_rn(acc[i][3]);
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (c < C && p < HW) dst[(size_t)p * C + c] = __float2half_rn(tile[threadIdx.x][i]);
     }
+}
+// Wsel[r][c] fp16, r in [0,256): rows 0..127 = W0[r][col0 + c], rows 128..255 = W3[r - 128][col3 + c]   (the latent columns of layers 0 and 3)
+__global__ void wsel_kernel(const float* __restrict__ w0, int ld0, int col0, const float* __restrict__ w3, int ld3, int col3, int C, __half* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 256 * C) return;
+    const int r = idx / C, c = idx % C;
+    out[idx] = __float2half_rn(r < 128 ? w0[(size_t)r * ld0 + col0 + c] : w3[(size_t)(r - 128) * ld3 + col3 + c]);
 }
 
 // ---- positional encoding of the camera-frame point (helper.py:121-125), tensor-core operand layout ----
@@ -1661,6 +1644,9 @@ static int make_window_tmap(CUtensorMap* out, void* base, int W, int H, int nv) 
     return NEO_OK;
 }
 
+int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* C, long long ldc, long long M, int N, int K,
+             int relu, cudaStream_t s);       // csrc/gemm_tc.cu
+
 int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
     using namespace tc;
     const NeoSceneDesc& d = sc->desc;
@@ -1668,6 +1654,25 @@ int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
     sc->tc_state = st;
     g_dbg = nullptr;
     const float* planes[3] = {d.planes_xz, d.planes_xy, d.planes_yz};
+    // channel-last fp16 copies of the raw feature maps (temporary: shared by the four MLPs' pre-projections) and the packed weight rows
+    struct Temps {                                   // freed on every exit path
+        __half* feat16[4] = {nullptr, nullptr, nullptr, nullptr};
+        __half* wsel = nullptr;
+        ~Temps() { for (int k = 0; k < 4; ++k) cudaFree(feat16[k]); cudaFree(wsel); }
+    } tmp;
+    __half** feat16 = tmp.feat16;
+    __half*& wsel = tmp.wsel;
+    {
+        const float* srcs[4] = {d.latent, planes[0], planes[1], planes[2]};
+        for (int k = 0; k < 4; ++k) {
+            const int C = k ? kWorldCh : kLocalCh, hw = k ? d.plane_h * d.plane_w : d.lat_h * d.lat_w;
+            NEO_CUDA(cudaMalloc(&feat16[k], (size_t)d.nv * hw * C * 2));
+            dim3 grid((hw + 31) / 32, (C + 31) / 32, d.nv), block(32, 8);
+            nchw_to_nhwc_f16_kernel<<<grid, block, 0, s>>>(srcs[k], feat16[k], C, hw);
+            NEO_LAUNCH_CHECK("nchw_to_nhwc_f16_kernel");
+        }
+        NEO_CUDA(cudaMalloc(&wsel, (size_t)256 * kLocalCh * 2));
+    }
     for (int i = 0; i < 4; ++i) {
         const NeoMLPParams& p = mlps[i];
         if (p.in_ch != 3 && p.in_ch != 4) { set_error("mlp %d: in_ch must be 3 or 4", i); return NEO_ERR_INVALID; }
@@ -1692,21 +1697,26 @@ int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
         NEO_LAUNCH_CHECK("head_kernel");
         m.headimg = (const uint4*)hb;
         m.bias = (const float*)bb;
-        // pre-projected feature maps [P0 | P3], stored as 64-channel groups [nv*4 + group][H][W][64] + their TMA descriptors
-        const float* srcs[4] = {d.latent, planes[0], planes[1], planes[2]};
+        // pre-projected feature maps [P0 | P3], stored as 64-channel groups [nv*4 + group][H][W][64] + their TMA descriptors.
+        // P = F . Wsel^T is a plain contraction over the raw channels: on tcgen05 through gemm_f16 (csrc/gemm_tc.cu), one N = 64 GEMM
+        // per (view, channel group) writing its plane of the grouped layout directly (fp16 features x fp16 weights, fp32 accumulate).
         for (int k = 0; k < 4; ++k) {
             const int C = k ? kWorldCh : kLocalCh, mh = k ? d.plane_h : d.lat_h, mw = k ? d.plane_w : d.lat_w, hw = mh * mw;
             const int col = m.enc_dim + (k ? kLocalCh : 0);
             void* pp = nullptr;
             if ((rc = scene_alloc_bytes(sc, &pp, (size_t)d.nv * hw * 256 * 2))) return rc;
             m.pmap[k] = (const __half*)pp;
-            dim3 gp((hw + 63) / 64, 2, d.nv);
-            preproject_kernel<<<gp, 256, 0, s>>>(srcs[k], C, hw, p.w0, in_dim, col, 0, (__half*)pp);
-            preproject_kernel<<<gp, 256, 0, s>>>(srcs[k], C, hw, p.w3, 128 + in_dim, 128 + col, 1, (__half*)pp);
-            NEO_LAUNCH_CHECK("preproject_kernel");
+            wsel_kernel<<<(256 * C + 255) / 256, 256, 0, s>>>(p.w0, in_dim, col, p.w3, 128 + in_dim, 128 + col, C, wsel);
+            NEO_LAUNCH_CHECK("wsel_kernel");
+            for (int v = 0; v < d.nv; ++v)
+                for (int g = 0; g < 4; ++g)
+                    if ((rc = gemm_f16(feat16[k] + (size_t)v * hw * C, C, wsel + (size_t)g * 64 * C, C, nullptr,
+                                       (__half*)pp + ((size_t)(v * 4 + g) * hw) * 64, 64, hw, 64, C, 0, s))) return rc;
             if ((rc = make_window_tmap(&m.tmap[k], pp, mw, mh, d.nv))) return rc;
         }
+        NEO_CUDA(cudaStreamSynchronize(s));          // wsel is reused by the next MLP
     }
+    NEO_CUDA(cudaStreamSynchronize(s));              // the temporaries are released when `tmp` goes out of scope
     return NEO_OK;
 }
 

@@ -168,6 +168,16 @@ extern "C" int neo_get_rays(int H, int W, float focal, const float* c2w, float* 
     if (H < 2 || W < 1 || !c2w) { set_error("neo_get_rays: bad arguments"); return NEO_ERR_INVALID; }
     return launch_get_rays(H, W, focal, c2w, o, vd, rd, radii, (cudaStream_t)stream);
 }
+extern "C" int neo_sample_rays(int n, const long long* pix_inds, int n_views, int H, int W, float focal, const float* c2w,
+                               const float* images, float* rays_o, float* viewdirs, float* rays_d, float* radii, float* target,
+                               int* err_flag, void* stream) {
+    if (n < 0 || n_views < 1 || H < 2 || W < 1 || !pix_inds || !c2w || !err_flag || (target && !images)) {
+        set_error("neo_sample_rays: bad arguments");
+        return NEO_ERR_INVALID;
+    }
+    return launch_sample_rays(n, pix_inds, n_views, H, W, focal, c2w, images, rays_o, viewdirs, rays_d, radii, target, err_flag,
+                              (cudaStream_t)stream);
+}
 extern "C" int neo_intersect_sphere(const float* o, const float* d, int n, float* far, int* err_flag, void* stream) {
     if (n <= 0) { set_error("neo_intersect_sphere: n_rays <= 0"); return NEO_ERR_INVALID; }
     return launch_far(o, d, n, far, err_flag, (cudaStream_t)stream);

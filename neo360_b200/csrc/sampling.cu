@@ -15,14 +15,9 @@ __device__ __forceinline__ void raw_dir(int i, int j, int H, int W, float focal,
     for (int r = 0; r < 3; ++r) d[r] = fmaf(c[2], c2w[r * 4 + 2], fmaf(c[1], c2w[r * 4 + 1], c[0] * c2w[r * 4 + 0]));
 }
 
-__global__ void get_rays_kernel(int H, int W, float focal, const float* __restrict__ c2w, float* __restrict__ o,
-                                float* __restrict__ vd, float* __restrict__ rd, float* __restrict__ radii) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= H * W) return;
-    int j = p / W, i = p % W;
-    float m[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) m[k] = c2w[k];
+// One pixel (i, j) of one view -> ray slot q.  Shared by the whole-frame and the sampled-pixel kernels so both give the same bits.
+__device__ __forceinline__ void ray_at(int i, int j, int H, int W, float focal, const float* m, size_t q, float* __restrict__ o,
+                                       float* __restrict__ vd, float* __restrict__ rd, float* __restrict__ radii) {
     float d[3];
     raw_dir(i, j, H, W, focal, m, d);
     if (radii) {
@@ -33,15 +28,25 @@ __global__ void get_rays_kernel(int H, int W, float focal, const float* __restri
         raw_dir(i, ja + 1, H, W, focal, m, b);
         float e[3] = {sub_(a[0], b[0]), sub_(a[1], b[1]), sub_(a[2], b[2])};
         float dx = __fsqrt_rn(dot3_(e, e));
-        radii[p] = __fdiv_rn(mul_(dx, 2.0f), __fsqrt_rn(12.0f));
+        radii[q] = __fdiv_rn(mul_(dx, 2.0f), __fsqrt_rn(12.0f));
     }
     float n = __fsqrt_rn(dot3_(d, d));
     for (int r = 0; r < 3; ++r) {
         float v = __fdiv_rn(d[r], n);   // quirk Q3: rays_d is normalised in place through the viewdirs alias
-        if (vd) vd[p * 3 + r] = v;
-        if (rd) rd[p * 3 + r] = v;
-        if (o) o[p * 3 + r] = m[r * 4 + 3];
+        if (vd) vd[q * 3 + r] = v;
+        if (rd) rd[q * 3 + r] = v;
+        if (o) o[q * 3 + r] = m[r * 4 + 3];
     }
+}
+
+__global__ void get_rays_kernel(int H, int W, float focal, const float* __restrict__ c2w, float* __restrict__ o,
+                                float* __restrict__ vd, float* __restrict__ rd, float* __restrict__ radii) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    float m[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = c2w[k];
+    ray_at(p % W, p / W, H, W, focal, m, (size_t)p, o, vd, rd, radii);
 }
 
 int launch_get_rays(int H, int W, float focal, const float* c2w, float* o, float* vd, float* rd, float* radii,
@@ -49,6 +54,33 @@ int launch_get_rays(int H, int W, float focal, const float* c2w, float* o, float
     int n = H * W;
     get_rays_kernel<<<(n + 255) / 256, 256, 0, s>>>(H, W, focal, c2w, o, vd, rd, radii);
     NEO_LAUNCH_CHECK("get_rays_kernel");
+    return NEO_OK;
+}
+
+// f3  training-batch pixel sampling (nerds360_ae.py:730-748): the reference builds all T x H x W rays of the target views on the
+// host and keeps `n` of them by `pix_inds`; here only the kept rays are ever computed.  pix indexes the flattened (T, H, W) stack.
+__global__ void sample_rays_kernel(int n, const long long* __restrict__ pix, int T, int H, int W, float focal,
+                                   const float* __restrict__ c2w, const float* __restrict__ images, float* __restrict__ o,
+                                   float* __restrict__ vd, float* __restrict__ rd, float* __restrict__ radii,
+                                   float* __restrict__ target, int* __restrict__ err) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    long long p = pix[q];
+    if (p < 0 || p >= (long long)T * H * W) { atomicExch(err, NEO_ERR_INVALID); return; }
+    int t = (int)(p / ((long long)H * W)), r = (int)(p % ((long long)H * W));
+    float m[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = c2w[t * 12 + k];
+    ray_at(r % W, r / W, H, W, focal, m, (size_t)q, o, vd, rd, radii);
+    if (target && images)
+        for (int c = 0; c < 3; ++c) target[(size_t)q * 3 + c] = images[(size_t)p * 3 + c];
+}
+
+int launch_sample_rays(int n, const long long* pix, int T, int H, int W, float focal, const float* c2w, const float* images,
+                       float* o, float* vd, float* rd, float* radii, float* target, int* err, cudaStream_t s) {
+    if (n == 0) return NEO_OK;
+    sample_rays_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, pix, T, H, W, focal, c2w, images, o, vd, rd, radii, target, err);
+    NEO_LAUNCH_CHECK("sample_rays_kernel");
     return NEO_OK;
 }
 

@@ -6,6 +6,7 @@
     sample_pdf              models/neo360/helper.py:218-249
     volumetric_rendering    models/neo360/helper.py:128-171
     get_rays                datasets/ray_utils.py:84-104,133-176
+    sample_rays             datasets/nerds360_ae.py:730-748 (pixel sampling of a training batch)
     index_grid / get_local_feats / field_eval   need a Scene (see renderer.py)
 
 CUDA only; there is no CPU fallback."""
@@ -48,6 +49,32 @@ def get_rays(H, W, focal, c2w, output_radii=True):
     with _on(m):
         L.check(lib.neo_get_rays(H, W, float(focal), L.ptr(m), L.ptr(o), L.ptr(vd), L.ptr(rd), L.ptr(rad), _stream()))
     return (o, vd, rd, rad) if output_radii else (o, vd, rd)
+
+
+def sample_rays(pix_inds, H, W, focal, c2w, images=None, check=True):
+    """The `pix_inds`-selected rays of the (T, H, W) stack of target views (nerds360_ae.py:730-748) without building the stack.
+    pix_inds (n) int64 CUDA, c2w (T,3,4) CUDA, images (T,H,W,3) fp32 CUDA or None -> rays_o, viewdirs, rays_d, radii (n,1), target."""
+    lib = L.load()
+    m = _f32(c2w[:, :3, :4])
+    if not pix_inds.is_cuda or pix_inds.dtype != torch.int64:
+        raise RuntimeError("sample_rays: pix_inds must be an int64 CUDA tensor")
+    pix = pix_inds.contiguous()
+    n, T = pix.numel(), m.shape[0]
+    img = None
+    if images is not None:
+        img = _f32(images)
+        if tuple(img.shape) != (T, H, W, 3):
+            raise ValueError(f"sample_rays: images must be ({T}, {H}, {W}, 3), got {tuple(img.shape)}")
+    o = torch.empty(n, 3, device=m.device); vd = torch.empty_like(o); rd = torch.empty_like(o)
+    rad = torch.empty(n, 1, device=m.device)
+    tgt = torch.empty(n, 3, device=m.device) if img is not None else None
+    err = torch.zeros(1, dtype=torch.int32, device=m.device)
+    with _on(m):
+        L.check(lib.neo_sample_rays(n, pix.data_ptr(), T, H, W, float(focal), L.ptr(m), L.ptr(img), L.ptr(o), L.ptr(vd), L.ptr(rd), L.ptr(rad),
+                                    L.ptr(tgt), L.ptr(err), _stream()))
+    if check and int(err.item()):   # the reference's fancy indexing raises IndexError synchronously
+        raise IndexError("sample_rays: pix_inds out of range")
+    return o, vd, rd, rad, tgt
 
 
 def intersect_sphere(rays_o, rays_d):

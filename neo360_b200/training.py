@@ -229,28 +229,50 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
     scope: its outputs are leaf tensors that receive gradients), targets = a fixed random image, Adam + clip 0.05 (model.py:1003-1025)."""
     import bench as Bm
     from . import NeRF_TP, synth
+    from .encoder import GridEncoder
+    with_encoder = not getattr(args, "freeze_encoder", False)
     sc = synth.make_scene((Bm.IMG_W, Bm.IMG_H), Bm.NV, (120, 160), seed=rank)
-    net = NeRF_TP(num_coarse_samples=Bm.N_COARSE, num_fine_samples=Bm.N_FINE, num_src_views=Bm.NV, precision="fp32")
-    net.load_state_dict(synth.make_mlp_params(0))
+    torch.manual_seed(0)                                        # identical initial weights on every rank (what DDP's broadcast gives)
+    enc = GridEncoder() if with_encoder else None
+    net = NeRF_TP(num_coarse_samples=Bm.N_COARSE, num_fine_samples=Bm.N_FINE, num_src_views=Bm.NV, precision="fp32", encoder=enc)
+    sd = net.state_dict()
+    sd.update(synth.make_mlp_params(0))
+    net.load_state_dict(sd)
     net = net.to(dev).train()
-    maps = {k: sc[k].to(dev).requires_grad_(True) for k in ("planes_xz", "planes_xy", "planes_yz", "latent")}
     cams = [sc[k].to(dev) for k in ("src_poses", "src_focal", "src_c")]
-    params = [p for m in net._mlps() for p in m.parameters()]
+    if with_encoder:
+        # the reference's training step (models/neo360/model.py:697-820): the encoder runs inside the step and trains through the renderer
+        g0 = torch.Generator().manual_seed(77 + rank)
+        src_imgs = (torch.rand(Bm.NV, 3, Bm.IMG_H, Bm.IMG_W, generator=g0) * 2 - 1).to(dev)
+        maps = {}
+        params = [p for p in net.parameters() if p.requires_grad]
+    else:
+        maps = {k: sc[k].to(dev).requires_grad_(True) for k in ("planes_xz", "planes_xy", "planes_yz", "latent")}
+        params = [p for m in net._mlps() for p in m.parameters()]
     opt = torch.optim.Adam(params, lr=5e-4)
     per = args.batch_rays // world
+    # dataset side (row f3): 20 target views of this rank's scene resident in HBM; per step the host draws `pix_inds` exactly like
+    # nerds360_ae.py:730-732 and the sampled rays + target colours are produced on the device (batches.train_batch)
+    from . import batches
     g = torch.Generator().manual_seed(1234 + rank)
-    host = []
-    for s in range(4):
-        o, d = Bm.frame_rays_cpu((7 * s + rank) % 100)
-        sel = torch.randint(0, o.shape[0], (per,), generator=g)
-        host.append((o[sel].contiguous().pin_memory(), d[sel].contiguous().pin_memory(), torch.rand(per, 3, generator=g).pin_memory()))
+    tposes = torch.stack([synth.target_pose((5 * k + rank) % 100, 100)[:3, :4] for k in range(batches.NUM_TARGET_VIEWS)]).to(dev)
+    timgs = torch.rand(batches.NUM_TARGET_VIEWS, Bm.IMG_H, Bm.IMG_W, 3, generator=g).to(dev)
+    views = batches.TargetViews(tposes, timgs, 0.8 * Bm.IMG_W)
+    pix_host = torch.empty(per, dtype=torch.int64).pin_memory()
     state = {}
 
     def step(s):
-        o, d, tgt = (x.to(dev, non_blocking=True) for x in host[s % len(host)])
-        net.set_scene(maps["planes_xz"], maps["planes_xy"], maps["planes_yz"], maps["latent"], *cams, sc["img_wh"], precisions=["fp32"])
-        ret = render_train(net, {"rays_o": o, "rays_d": d, "viewdirs": d, "src_poses": cams[0]},
-                           [maps["planes_xz"], maps["planes_xy"], maps["planes_yz"]], maps["latent"], True, False)
+        pix_host.copy_(batches.draw_pix_inds(views.T, views.H, views.W, per, g))
+        src = {"src_poses": cams[0], "src_focal": cams[1], "src_c": cams[2]}
+        if with_encoder:
+            src["src_imgs"] = src_imgs
+        else:
+            src["src_imgs"] = torch.empty(Bm.NV, 3, Bm.IMG_H, Bm.IMG_W, device="meta")      # only its shape is read (image size)
+        batch = batches.train_batch(views, src, pix_inds=pix_host)
+        if not with_encoder:
+            batch.update(maps)
+        tgt = batch["target"]
+        ret = net(batch, True, False, None, None, out_depth=False)
         loss = training_loss(ret, tgt)
         opt.zero_grad(set_to_none=True)
         for t in maps.values():
@@ -275,6 +297,10 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
                                     "MSE + distortion loss, backward, NCCL gradient all-reduce, clip 0.05, Adam",
                         "batch_rays": per * world, "rays_per_rank": per, "samples": "128+64", "precision": "fp32 (reference formulation)",
                         "parallelism": f"data parallel x{world}: one all-reduce over a flat {state['grad_elems']}-element gradient slab per step",
-                        "hand_written": "sampling, lookups fwd/bwd, compositing fwd/bwd", "library": "dense layers (autograd GEMMs), Adam"},
-                e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": per * 9 * 4, "d2h_bytes_per_step": 4},
+                        "encoder": "GridEncoder inside the step (framework ops under autograd), its gradients in the all-reduced slab" if with_encoder
+                                   else "frozen / absent: encoder outputs are leaf tensors (finetune mode, model.py:969-979)",
+                        "batch": "pix_inds drawn on the host as the reference dataset does, rays + targets of the sampled pixels generated on the device "
+                                 "from 20 resident target views (neo_sample_rays)",
+                        "hand_written": "pixel sampling, ray sampling, lookups fwd/bwd, compositing fwd/bwd", "library": "dense layers and encoder (autograd), Adam"},
+                e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": 4},
                 final_loss=loss, clocks=sampler.result() if sampler else None)

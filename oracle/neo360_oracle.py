@@ -51,6 +51,16 @@ def rays_from_pose(directions: Tensor, c2w: Tensor):
     return o.reshape(-1, 3).contiguous(), d, d, radii
 
 
+def sample_training_rays(pix_inds: Tensor, H: int, W: int, focal: float, poses: Tensor, images: Tensor = None):
+    """The pixel sampling of the training `__getitem__` (datasets/nerds360_ae.py:684-748): every ray of every target view is built,
+    stacked (T, H*W, .), flattened and indexed by `pix_inds`.  Returns rays_o, viewdirs, rays_d, radii (n,1), target (n,3) or None."""
+    dirs = ray_directions(H, W, focal)
+    per_view = [rays_from_pose(dirs, c2w[:3, :4]) for c2w in poses]
+    o, vd, rd, radii = (torch.stack([v[k] for v in per_view], 0) for k in range(4))
+    tgt = None if images is None else images.reshape(-1, 3)[pix_inds]
+    return o.reshape(-1, 3)[pix_inds], vd.reshape(-1, 3)[pix_inds], rd.reshape(-1, 3)[pix_inds], radii.reshape(-1, 1)[pix_inds], tgt
+
+
 # --------------------------------------------------------------------------------------------
 # a3  ray / unit-sphere intersection                         models/neo360/helper.py:253-273
 # --------------------------------------------------------------------------------------------

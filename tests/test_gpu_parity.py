@@ -41,6 +41,50 @@ def test_get_rays(cuda):
         assert md(o, ro) == 0 and md(vd, rvd) < 2e-7 and md(rd, rrd) < 2e-7 and md(rad, rrad) < 2e-7   # row-difference cancellation amplifies matmul rounding
 
 
+def test_sample_rays_training_batch(cuda):
+    """f3 (nerds360_ae.py:730-764): sampled-pixel rays are bit-identical to the same pixels of the whole-frame generator, match the oracle's
+    build-everything-then-index restatement, and the batch dict carries the reference's keys."""
+    from neo360_b200 import batches, ops
+    Tn, H, W, focal = 5, 48, 64, 51.2
+    poses = torch.stack([synth.target_pose(3 * k + 1, 100)[:3, :4] for k in range(Tn)])
+    g = torch.Generator().manual_seed(5)
+    images = torch.rand(Tn, H, W, 3, generator=g)
+    pix = batches.draw_pix_inds(Tn, H, W, 500, torch.Generator().manual_seed(9))
+    assert torch.equal(pix, torch.randint(0, Tn * H * W, (500,), generator=torch.Generator().manual_seed(9)))   # the reference's own draw
+    pix[:4] = torch.tensor([0, W - 1, Tn * H * W - 1, (H - 1) * W])                                                # corners, last row (radii quirk)
+    o, vd, rd, rad, tgt = ops.sample_rays(pix.to(cuda), H, W, focal, poses.to(cuda), images.to(cuda))
+    full = [ops.get_rays(H, W, focal, p.to(cuda)) for p in poses]
+    for got, k in ((o, 0), (vd, 1), (rd, 2)):
+        assert torch.equal(got, torch.cat([f[k] for f in full], 0)[pix.to(cuda)])
+    assert torch.equal(rad[:, 0], torch.cat([f[3] for f in full], 0)[pix.to(cuda)])
+    assert torch.equal(tgt.cpu(), images.reshape(-1, 3)[pix])
+    ro, rvd, rrd, rrad, rtgt = orc.sample_training_rays(pix, H, W, focal, poses, images)
+    assert md(o, ro) == 0 and md(vd, rvd) < 2e-7 and md(rd, rrd) < 2e-7 and md(rad, rrad) < 2e-7 and md(tgt, rtgt) == 0
+    with pytest.raises(IndexError):
+        ops.sample_rays(torch.tensor([Tn * H * W], device=cuda), H, W, focal, poses.to(cuda))
+    assert ops.sample_rays(torch.empty(0, dtype=torch.int64, device=cuda), H, W, focal, poses.to(cuda))[0].shape == (0, 3)
+    views = batches.TargetViews(poses.to(cuda), images.to(cuda), focal)
+    src = {"src_imgs": torch.zeros(3, 3, H, W, device=cuda), "src_poses": torch.zeros(3, 4, 4, device=cuda),
+           "src_focal": torch.zeros(3, device=cuda), "src_c": torch.zeros(3, 2, device=cuda)}
+    b = batches.train_batch(views, src, generator=torch.Generator().manual_seed(9))
+    assert list(b) == ["src_imgs", "src_poses", "src_focal", "src_c", "instance_mask", "rays_o", "rays_d", "viewdirs", "target", "nocs_2d",
+                       "radii", "multloss", "normals"]                                                          # nerds360_ae.py:750-764
+    assert b["rays_o"].shape == (500, 3) and b["radii"].shape == (500, 1) and b["multloss"].shape == (500, 1)
+    assert torch.equal(b["rays_o"][4:], o[4:]) and torch.equal(b["target"][4:], tgt[4:])
+
+
+def test_sample_rays_golden(cuda):
+    """Row f3 against the unmodified reference's vectors (tests/golden/train_batch_vectors.npz, oracle/make_golden_batch.py)."""
+    import os
+    from neo360_b200 import ops
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_batch_vectors.npz"))
+    Tn, H, W = int(z["T"]), int(z["H"]), int(z["W"])
+    images = torch.rand(Tn, H, W, 3, generator=torch.Generator().manual_seed(int(z["seed"])))
+    o, vd, rd, rad, tgt = ops.sample_rays(T(z["pix_inds"]).to(cuda), H, W, float(z["focal"]), T(z["poses"]).to(cuda), images.to(cuda))
+    assert md(o, T(z["rays_o"])) == 0 and md(tgt, T(z["target"])) == 0
+    assert md(vd, T(z["viewdirs"])) < 2e-7 and md(rd, T(z["rays_d"])) < 2e-7 and md(rad, T(z["radii"])) < 2e-7
+
+
 def test_intersect_and_coarse_sampling(cuda, golden):
     from neo360_b200 import ops
     o, d = T(golden["kat_o"]), T(golden["kat_d"])

@@ -140,3 +140,17 @@ def test_mip360_oracle_vs_reference_vectors(tag):
         for k in ("density", "rgb", "sdist", "weights"):
             assert md(hist[i][k], g[f"{tag}_hist{i}_{k}"]) < 1e-4, (i, k)
         assert md(hist_r[i]["sdist"], g[f"{tag}_rhist{i}_sdist"]) < 1e-5
+
+
+def test_training_batch_golden():
+    """Row f3: the oracle's pixel sampling equals the reference's get_rays + stack + index (oracle/make_golden_batch.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import neo360_oracle as orc
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_batch_vectors.npz"))
+    pix, poses = torch.from_numpy(z["pix_inds"]), torch.from_numpy(z["poses"])
+    images = torch.rand(int(z["T"]), int(z["H"]), int(z["W"]), 3, generator=torch.Generator().manual_seed(int(z["seed"])))
+    o, vd, rd, rad, tgt = orc.sample_training_rays(pix, int(z["H"]), int(z["W"]), float(z["focal"]), poses, images)
+    for name, mine in (("rays_o", o), ("viewdirs", vd), ("rays_d", rd), ("radii", rad), ("target", tgt)):
+        assert mine.shape == z[name].shape and float((mine - torch.from_numpy(z[name])).abs().max()) <= 1.2e-7, name
