@@ -54,6 +54,9 @@ def parse():
                          "Mip-NeRF 360 at 640x480 with 64+64+64 samples, every dense layer on tcgen05")
     ap.add_argument("--views", type=int, default=100, help="turntable mode: number of target views")
     ap.add_argument("--batch-rays", type=int, default=4096, help="train mode: rays per optimisation step over all ranks")
+    ap.add_argument("--train-matmul", choices=("fp32", "tf32"), default="fp32",
+                    help="train mode: precision of the framework GEMMs of the dense layers.  tf32 = torch.backends.cuda.matmul.allow_tf32, the setting "
+                         "the reference was trained under (torch 1.11 default, SURVEY.md 8(d))")
     ap.add_argument("--freeze-encoder", action="store_true", help="train mode: MLPs only (finetune mode); default trains GridEncoder inside the step")
     return ap.parse_args()
 

@@ -85,6 +85,9 @@ int neo_scene_create(const NeoSceneDesc* desc, const NeoMLPParams mlps[4], int p
 void neo_scene_free(NeoScene* scene);
 /* bytes of device memory held by the scene */
 size_t neo_scene_bytes(const NeoScene* scene);
+/* neo_scene_free keeps the device blocks of a destroyed scene (per device, up to 6 GB in total) for the next scene of the same shape, so
+ * that a scene change costs its kernels and not cudaMalloc / cudaFree.  This returns every kept block to the driver. */
+void neo_release_cached(void);
 
 /* rays of one call: rays["rays_o"|"rays_d"|"viewdirs"] (nerds360_ae.py:1007-1023). */
 typedef struct {

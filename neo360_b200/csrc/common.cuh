@@ -193,13 +193,17 @@ struct NeoScene {
     neo::MLPFp32 mlp32[4];
     void* tc_state;            // opaque state of the tensor-core path (field_tc.cu)
     int* err_flag;             // device int
-    std::vector<void*> allocations;
+    std::vector<std::pair<void*, size_t>> allocations;
     size_t bytes;
 };
 
 namespace neo {
 // scene.cu
 int scene_alloc_bytes(NeoScene* sc, void** p, size_t bytes);
+// Device blocks of destroyed scenes (and the scene builder's temporaries) are kept, per device and up to a cap, for the next scene of
+// the same shape: a scene change then costs its kernels, not cudaMalloc / cudaFree (which are slow, erratic and device-synchronising).
+int pool_alloc(void** p, size_t bytes);
+void pool_release(void* p, size_t bytes);
 // sampling.cu
 int launch_far(const float* o, const float* d, int n, float* far, int* err, cudaStream_t s);
 int launch_sample_coarse(const float* o, const float* d, const float* far, int n, int num_samples, int in_sphere,

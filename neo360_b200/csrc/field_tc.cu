@@ -1655,23 +1655,32 @@ int tc_scene_create(NeoScene* sc, const NeoMLPParams mlps[4], cudaStream_t s) {
     g_dbg = nullptr;
     const float* planes[3] = {d.planes_xz, d.planes_xy, d.planes_yz};
     // channel-last fp16 copies of the raw feature maps (temporary: shared by the four MLPs' pre-projections) and the packed weight rows
-    struct Temps {                                   // freed on every exit path
+    struct Temps {                                   // handed back to the block pool on every exit path (after the stream has drained)
         __half* feat16[4] = {nullptr, nullptr, nullptr, nullptr};
+        size_t bytes[4] = {0, 0, 0, 0};
         __half* wsel = nullptr;
-        ~Temps() { for (int k = 0; k < 4; ++k) cudaFree(feat16[k]); cudaFree(wsel); }
+        cudaStream_t s;
+        ~Temps() {
+            cudaStreamSynchronize(s);
+            for (int k = 0; k < 4; ++k) pool_release(feat16[k], bytes[k]);
+            pool_release(wsel, (size_t)256 * kLocalCh * 2);
+        }
     } tmp;
+    tmp.s = s;
     __half** feat16 = tmp.feat16;
     __half*& wsel = tmp.wsel;
     {
         const float* srcs[4] = {d.latent, planes[0], planes[1], planes[2]};
+        int rc;
         for (int k = 0; k < 4; ++k) {
             const int C = k ? kWorldCh : kLocalCh, hw = k ? d.plane_h * d.plane_w : d.lat_h * d.lat_w;
-            NEO_CUDA(cudaMalloc(&feat16[k], (size_t)d.nv * hw * C * 2));
+            tmp.bytes[k] = (size_t)d.nv * hw * C * 2;
+            if ((rc = pool_alloc((void**)&feat16[k], tmp.bytes[k]))) return rc;
             dim3 grid((hw + 31) / 32, (C + 31) / 32, d.nv), block(32, 8);
             nchw_to_nhwc_f16_kernel<<<grid, block, 0, s>>>(srcs[k], feat16[k], C, hw);
             NEO_LAUNCH_CHECK("nchw_to_nhwc_f16_kernel");
         }
-        NEO_CUDA(cudaMalloc(&wsel, (size_t)256 * kLocalCh * 2));
+        if ((rc = pool_alloc((void**)&wsel, (size_t)256 * kLocalCh * 2))) return rc;
     }
     for (int i = 0; i < 4; ++i) {
         const NeoMLPParams& p = mlps[i];

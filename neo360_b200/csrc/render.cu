@@ -171,6 +171,7 @@ extern "C" int neo_get_rays(int H, int W, float focal, const float* c2w, float* 
 extern "C" int neo_sample_rays(int n, const long long* pix_inds, int n_views, int H, int W, float focal, const float* c2w,
                                const float* images, float* rays_o, float* viewdirs, float* rays_d, float* radii, float* target,
                                int* err_flag, void* stream) {
+    if (n == 0) return NEO_OK;                     // an empty batch is valid (and its buffers may be null)
     if (n < 0 || n_views < 1 || H < 2 || W < 1 || !pix_inds || !c2w || !err_flag || (target && !images)) {
         set_error("neo_sample_rays: bad arguments");
         return NEO_ERR_INVALID;

@@ -5,6 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace neo {
 
@@ -66,12 +69,64 @@ __global__ void scalar_fetch_kernel(const float* focal, const float* c, float* o
     out[0] = focal[0]; out[1] = c[0]; out[2] = c[1];
 }
 
+// ---- block pool ----
+namespace {
+struct BlockPool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;     // (device, bytes) -> block
+    size_t held = 0;
+};
+BlockPool g_pool;
+constexpr size_t kPoolCap = 6ull << 30;       // bytes kept across all devices; beyond it blocks go back to the driver
+constexpr size_t kPoolMinBlock = 1 << 16;     // small blocks are not worth keeping
+}  // namespace
+
+int pool_alloc(void** p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes >= kPoolMinBlock) {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        auto it = g_pool.free_blocks.find({dev, bytes});
+        if (it != g_pool.free_blocks.end()) {
+            *p = it->second;
+            g_pool.free_blocks.erase(it);
+            g_pool.held -= bytes;
+            return NEO_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {                   // give the cached blocks back and retry once
+        cudaGetLastError();
+        neo_release_cached();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scene)");
+    return NEO_OK;
+}
+
+// The caller guarantees that no kernel still uses the block (neo_scene_free synchronises the device first, as cudaFree would).
+void pool_release(void* p, size_t bytes) {
+    if (!p) return;
+    int dev = 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device; else cudaGetLastError();
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        if (bytes >= kPoolMinBlock && g_pool.held + bytes <= kPoolCap) {
+            g_pool.free_blocks.insert({{dev, bytes}, p});
+            g_pool.held += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
 template <typename T>
 static int dev_alloc(NeoScene* sc, T** p, size_t count) {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scene)");
-    sc->allocations.push_back(q);
+    int rc = pool_alloc(&q, count * sizeof(T));
+    if (rc) return rc;
+    sc->allocations.push_back({q, count * sizeof(T)});
     sc->bytes += count * sizeof(T);
     *p = reinterpret_cast<T*>(q);
     return NEO_OK;
@@ -215,8 +270,20 @@ extern "C" int neo_scene_create(const NeoSceneDesc* d, const NeoMLPParams mlps[4
 extern "C" void neo_scene_free(NeoScene* sc) {
     if (!sc) return;
     tc_scene_free(sc);
-    for (void* p : sc->allocations) cudaFree(p);
+    cudaDeviceSynchronize();                       // what cudaFree would do implicitly: nothing may still read the blocks
+    for (auto& a : sc->allocations) pool_release(a.first, a.second);
     delete sc;
+}
+
+extern "C" void neo_release_cached(void) {
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (auto& kv : g_pool.free_blocks) blocks.push_back(kv.second);
+        g_pool.free_blocks.clear();
+        g_pool.held = 0;
+    }
+    for (void* p : blocks) cudaFree(p);
 }
 
 extern "C" size_t neo_scene_bytes(const NeoScene* sc) { return sc ? sc->bytes : 0; }

@@ -231,6 +231,9 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
     from . import NeRF_TP, synth
     from .encoder import GridEncoder
     with_encoder = not getattr(args, "freeze_encoder", False)
+    tf32 = getattr(args, "train_matmul", "fp32") == "tf32"
+    torch.backends.cuda.matmul.allow_tf32 = tf32                # forward and backward GEMMs of the dense layers (and the encoder's linears)
+    torch.backends.cudnn.allow_tf32 = tf32                      # encoder convolutions
     sc = synth.make_scene((Bm.IMG_W, Bm.IMG_H), Bm.NV, (120, 160), seed=rank)
     torch.manual_seed(0)                                        # identical initial weights on every rank (what DDP's broadcast gives)
     enc = GridEncoder() if with_encoder else None
@@ -292,10 +295,11 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
     loss = float(state["loss"].item())
     rays = per * world * args.steps
     return dict(base, metric="training rays/sec, neo360 generalisable training, 4096-ray batches", value=rays / (ms * 1e-3),
-                ms_per_step=ms / args.steps, scaling="strong", dtype="f32",
+                ms_per_step=ms / args.steps, scaling="strong", dtype="tf32" if tf32 else "f32",
                 config={"workload": "neo360 training step (BASELINE configs[3]): stratified + PDF sampling, lookups, NeRFPPMLP x4, compositing, "
                                     "MSE + distortion loss, backward, NCCL gradient all-reduce, clip 0.05, Adam",
-                        "batch_rays": per * world, "rays_per_rank": per, "samples": "128+64", "precision": "fp32 (reference formulation)",
+                        "batch_rays": per * world, "rays_per_rank": per, "samples": "128+64",
+                        "precision": "fp32 (reference formulation)" + ("; framework GEMMs / convolutions in TF32 (the reference's torch-1.11 default)" if tf32 else ""),
                         "parallelism": f"data parallel x{world}: one all-reduce over a flat {state['grad_elems']}-element gradient slab per step",
                         "encoder": "GridEncoder inside the step (framework ops under autograd), its gradients in the all-reduced slab" if with_encoder
                                    else "frozen / absent: encoder outputs are leaf tensors (finetune mode, model.py:969-979)",

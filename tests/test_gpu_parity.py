@@ -779,3 +779,38 @@ def test_scene_cache_is_keyed_by_identity_and_parameter_version(cuda):
         ref2 = orc.render(rays, osc, P2, nc, nf, False, True)[1][0]
     net.check()
     assert md(a, b) > 1e-3 and md(b, ref2) < 2e-4, (md(a, b), md(b, ref2))
+
+
+def test_scene_block_pool_recycles_without_stale_data(cuda):
+    """Scene changes recycle the device blocks of the destroyed scene (neo_scene_free -> pool -> neo_scene_create).  A recycled block
+    holds the PREVIOUS scene's packed maps: every scene must still render its own data (tc and fp32 against the oracle), and
+    `release_cached` must hand the blocks back."""
+    import neo360_b200
+    from neo360_b200 import NeRF_TP
+    W, H, nc, nf = 64, 48, 12, 6
+    P = synth.make_mlp_params(5)
+    rays = {k: v[500:500 + 64].contiguous() for k, v in _frame_rays(W, H).items()}
+    cr = {k: v.to(cuda) for k, v in rays.items()}
+    for prec, tol in (("tc", 3e-2), ("fp32", 2e-4)):
+        net = NeRF_TP(num_coarse_samples=nc, num_fine_samples=nf, precision=prec).eval()
+        net.load_state_dict(P)
+        net = net.to(cuda)
+        sizes = []
+        for seed in (21, 22, 23):
+            sc = synth.make_scene((W, H), 3, (24, 32), seed)
+            net.set_scene(*[sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")],
+                          sc["img_wh"])                       # destroys the previous scene: same shapes, so its blocks are reused
+            sizes.append(net._scene.nbytes)
+            osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                            float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+            with torch.no_grad():
+                got = net(cr, False, False, None, None, out_depth=True)[1]
+                ref = orc.render(rays, osc, P, nc, nf, False, True)[1]
+            net.check()
+            assert md(got[0], ref[0]) < tol, (prec, seed, md(got[0], ref[0]))
+        assert sizes[0] == sizes[1] == sizes[2]
+        del net
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    neo360_b200.release_cached()
+    assert torch.cuda.mem_get_info()[0] >= free0
