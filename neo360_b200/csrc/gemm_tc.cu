@@ -7,9 +7,12 @@
 // 192 threads: warp 0 = TMA producer (one lane), warp 1 = MMA issue (one lane) + TMEM allocation, warps 2-5 = epilogue (TMEM lane
 // quarter warp % 4).  4-stage shared-memory ring (A 128 x 64, W BN x 64 per stage), two TMEM accumulators (2 x BN columns) so the
 // epilogue of tile i (tcgen05.ld -> bias -> ReLU -> fp16 -> 64-byte row segments to global) overlaps the MMAs of tile i + 1.
+// Large problems with N % 256 == 0 (the 1024- and 256-wide layers over millions of rows) run the CTA-pair variant further down
+// (gemm_f16_pair_kernel: tcgen05.mma.cta_group::2, 256 x 256 tiles, 6-stage ring); the single-CTA kernel serves everything else.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace neo {
 namespace gemm {
@@ -193,6 +196,157 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): the two SMs of a cluster of 2 compute ONE 256 x 256 tile.  Each CTA stages its own 128 rows of A and
+// HALF of the W tile (128 of the 256 output columns); the pair's tensor cores read both halves of W, so per MMA cycle each SM pulls
+// 32 KB instead of 48 KB through L2 -> SM (the single-CTA kernel is bound there: ncu r2, 54 % tensor pipe at 3.5 TB/s DRAM).
+// Protocol (CUTLASS sm100 2-SM pipeline semantics, cutlass/pipeline/sm100_pipeline.hpp):
+//   * both CTAs issue their TMA loads with .cta_group::2; the transaction bytes of BOTH land on the LEADER's FULL barrier (peer bit of
+//     the barrier address cleared), which the leader arms with the pair's total byte count;
+//   * only the leader (cluster rank 0) issues tcgen05.mma.cta_group::2; tcgen05.commit.cta_group::2 with multicast mask 0b11 releases
+//     the shared-memory stage in both CTAs and publishes the accumulator to both epilogues;
+//   * each CTA's epilogue drains its own 128 TMEM lanes (its 128 rows x 256 columns) and arrives on the leader's ACC_EMPTY barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6, BN2 = 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address: "the even CTA of the pair"
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t n_clusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(leader_bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {          // arrives on `bar` of BOTH CTAs when the pair's MMAs so far are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
+                     __half* __restrict__ C, long long M, int N, int K, long long ldc, int relu) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    constexpr uint32_t A_BYTES = BM * BK * 2, W_BYTES = (BN2 / 2) * BK * 2, STAGE = A_BYTES + W_BYTES;
+    const uint32_t bar0 = sbase + kStages2 * STAGE;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (kStages2 + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * kStages2 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * kStages2 + 2 + a); };
+    const uint32_t tmem_slot_addr = bar0 + 8u * (2 * kStages2 + 4);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kStages2 * STAGE + 8 * (2 * kStages2 + 4));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 8); }     // 4 epilogue warps x 2 CTAs (leader's copy is the live one)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // the peer's barriers are initialised before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_tiles_n = N / BN2;
+    const long long n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * n_tiles_n;
+    const int kblocks = K / BK;
+    const long long cid = cluster_id_x(), ncl = n_clusters_x();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = cid; tile < n_tiles; tile += ncl) {
+                const long long m0 = (tile / n_tiles_n) * (2 * BM) + (long long)rank * BM;
+                const int n0 = (int)(tile % n_tiles_n) * BN2 + (int)rank * (BN2 / 2);
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    mbar_wait(EMPTY(s), ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(FULL(s), 2 * STAGE);
+                    tma_load_2d_pair(sbase + s * STAGE, &tmA, kb * BK, (int)m0, FULL(s));
+                    tma_load_2d_pair(sbase + s * STAGE + A_BYTES, &tmW, kb * BK, n0, FULL(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            uint32_t it = 0, tcount = 0;
+            constexpr uint32_t idesc = idesc_f16(2 * BM, BN2);
+            for (long long tile = cid; tile < n_tiles; tile += ncl, ++tcount) {
+                const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+                mbar_wait(ACC_EMPTY(acc), aph ^ 1u);                 // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BN2;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    mbar_wait(FULL(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = sbase + s * STAGE, sw = sa + A_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks)
+                        mma_ss_pair(d, desc_sw128(sa + ks * 32), desc_sw128(sw + ks * 32), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    tc_commit_pair(EMPTY(s));
+                }
+                tc_commit_pair(ACC_FULL(acc));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tcount = 0;
+        for (long long tile = cid; tile < n_tiles; tile += ncl, ++tcount) {
+            const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+            const long long m0 = (tile / n_tiles_n) * (2 * BM) + (long long)rank * BM;
+            const int n0 = (int)(tile % n_tiles_n) * BN2;
+            const long long row = m0 + q * 32 + lane;
+            mbar_wait(ACC_FULL(acc), aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN2 / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + acc * BN2 + c * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+                    uint4* dst = reinterpret_cast<uint4*>(C + row * ldc + n0 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float x = __uint_as_float(r[8 * j + i]) + (bias ? __ldg(bias + n0 + c * 32 + 8 * j + i) : 0.f);
+                            v[i] = relu ? fmaxf(x, 0.f) : x;
+                        }
+                        dst[j] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // neither CTA frees tensor memory (or exits) while its peer may still touch the pair's state
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // out[r][c] = fp16(in[r][c]) for c < cols_in, 0 for cols_in <= c < cols_out          (weight / activation packing with K padding)
 __global__ void f32_to_f16_pad_kernel(const float* __restrict__ in, long long rows, int cols_in, long long ld_in, __half* __restrict__ out,
                                       int cols_out, long long ld_out) {
@@ -246,6 +400,22 @@ static int launch(const __half* A, long long lda, const __half* W, long long ldw
     return NEO_OK;
 }
 
+static int launch_pair(const __half* A, long long lda, const __half* W, long long ldw, const float* bias, __half* C, long long ldc, long long M,
+                       int N, int K, int relu, int n_sm, cudaStream_t s) {
+    alignas(64) CUtensorMap tmA, tmW;
+    int rc;
+    if ((rc = make_tmap_2d(&tmA, A, M, K, lda, BM))) return rc;
+    if ((rc = make_tmap_2d(&tmW, W, N, K, ldw, BN2 / 2))) return rc;
+    const long long tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
+    const long long pairs = n_sm / 2;
+    const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
+    const size_t smem = (size_t)kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 8 * (2 * kStages2 + 4) + 16 + 1024;
+    NEO_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_f16_pair_kernel<<<grid, kThreads, smem, s>>>(tmA, tmW, bias, C, M, N, K, ldc, relu);
+    NEO_LAUNCH_CHECK("gemm_f16_pair_kernel");
+    return NEO_OK;
+}
+
 }  // namespace gemm
 
 // C (M x N, row stride ldc) = act(A (M x K, row stride lda) . W (N x K, row stride ldw)^T + bias); fp16 in / out, fp32 accumulate.
@@ -259,7 +429,20 @@ int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const f
     }
     const __half *a = (const __half*)A, *w = (const __half*)W;
     __half* c = (__half*)C;
-    if (N % 256 == 0) return launch<256>(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, s);
+    if (N % 256 == 0) {
+        // CTA pairs (256 x 256 tiles) once there is a tile for every pair of SMs; NEO_GEMM_PAIR=0 keeps the single-CTA kernel (A/B runs)
+        static int use_pair = -1, n_sm = 0;
+        if (use_pair < 0) {
+            const char* e = getenv("NEO_GEMM_PAIR");
+            use_pair = !(e && e[0] == '0');
+            int dev = 0;
+            NEO_CUDA(cudaGetDevice(&dev));
+            NEO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const long long tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * (N / 256);
+        if (use_pair && tiles2 >= n_sm / 2) return launch_pair(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, n_sm, s);
+        return launch<256>(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, s);
+    }
     if (N % 128 == 0) return launch<128>(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, s);
     return launch<64>(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, s);
 }
