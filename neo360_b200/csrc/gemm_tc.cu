@@ -6,7 +6,8 @@
 // One persistent CTA per SM walks (m-tile, n-tile) pairs, n fastest so the CTAs working at the same time share A tiles in L2.
 // 192 threads: warp 0 = TMA producer (one lane), warp 1 = MMA issue (one lane) + TMEM allocation, warps 2-5 = epilogue (TMEM lane
 // quarter warp % 4).  4-stage shared-memory ring (A 128 x 64, W BN x 64 per stage), two TMEM accumulators (2 x BN columns) so the
-// epilogue of tile i (tcgen05.ld -> bias -> ReLU -> fp16 -> 64-byte row segments to global) overlaps the MMAs of tile i + 1.
+// epilogue of tile i (tcgen05.ld -> bias -> ReLU -> fp16 -> per-warp shared-memory transpose -> whole 128-byte lines to global)
+// overlaps the MMAs of tile i + 1.
 // Large problems with N % 256 == 0 (the 1024- and 256-wide layers over millions of rows) run the CTA-pair variant further down
 // (gemm_f16_pair_kernel: tcgen05.mma.cta_group::2, 256 x 256 tiles, 6-stage ring); the single-CTA kernel serves everything else.
 #include "common.cuh"
@@ -88,6 +89,48 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Epilogue of one warp for one accumulator tile: its 32 TMEM lanes (rows) x NCOLS columns -> bias -> ReLU -> fp16 -> global.
+// A lane owns a ROW of the accumulator, so storing straight from registers would touch 32 different rows per instruction (32 partial
+// sectors each).  Instead every 64 columns are transposed through a 4 KB per-warp staging tile ([32 rows][128 B], 16-byte pieces
+// XOR-swizzled by row: conflict-free both ways) and leave as whole 128-byte lines, 4 rows per store instruction.
+constexpr uint32_t kEpiStage = 32 * 128;           // bytes per epilogue warp
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_lanes /*lane base + accumulator column*/, uint32_t stage, const float* __restrict__ bias,
+                                              __half* __restrict__ C, long long ldc, long long row0 /*first of the warp's 32 rows*/, long long M,
+                                              int n0, int relu, int lane) {
+#pragma unroll 1
+    for (int cc = 0; cc < NCOLS / 64; ++cc) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(tmem_lanes + cc * 64 + h * 32, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float x = __uint_as_float(r[8 * j + i]) + (bias ? __ldg(bias + n0 + cc * 64 + h * 32 + 8 * j + i) : 0.f);
+                    v[i] = relu ? fmaxf(x, 0.f) : x;
+                }
+                const uint32_t piece = (uint32_t)(4 * h + j) ^ (uint32_t)(lane & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + piece * 16), "r"(pack_h2(v[0], v[1])),
+                             "r"(pack_h2(v[2], v[3])), "r"(pack_h2(v[4], v[5])), "r"(pack_h2(v[6], v[7])) : "memory");
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), p = lane & 7;
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(stage + rr * 128 + ((p ^ (rr & 7)) * 16)) : "memory");
+            if (row0 + rr < M) *reinterpret_cast<uint4*>(C + (row0 + rr) * ldc + n0 + cc * 64 + p * 8) = val;
+        }
+        __syncwarp();
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
@@ -103,6 +146,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kStages * STAGE + 8 * (2 * kStages + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t epi_stage = sbase + ((kStages * STAGE + 8 * (2 * kStages + 4) + 16 + 127) & ~127u) + (warp & 3) * kEpiStage;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
@@ -164,28 +208,108 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
             const long long m0 = (tile / n_tiles_n) * BM;
             const int n0 = (int)(tile % n_tiles_n) * BN;
-            const long long row = m0 + q * 32 + lane;
             mbar_wait(ACC_FULL(acc), aph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(lane_base + acc * BN + c * 32, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-                    uint4* dst = reinterpret_cast<uint4*>(C + row * ldc + n0 + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float x = __uint_as_float(r[8 * j + i]) + (bias ? __ldg(bias + n0 + c * 32 + 8 * j + i) : 0.f);
-                            v[i] = relu ? fmaxf(x, 0.f) : x;
-                        }
-                        dst[j] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    }
+            epilogue_rows<BN>(lane_base + acc * BN, epi_stage, bias, C, ldc, m0 + q * 32, M, n0, relu, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-stationary variant for the 256-wide layers (N == 256, K <= 256: vanilla NeRF's 8 x 256 trunk, the Mip-NeRF 360 proposal
+// MLPs): the whole weight matrix (<= 128 KB fp16) is loaded into shared memory ONCE per CTA and only the activation tiles stream through
+// the ring.  These layers are activation-bandwidth bound (1 KB of HBM traffic per 131 kFLOP row); re-fetching the 128 KB weight tile for
+// every 64 KB activation tile, as the generic kernels do, triples the L2 -> SM traffic for nothing.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStagesWS = 5, BNW = 256;
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
+                   __half* __restrict__ C, long long M, int K, long long ldc, int relu) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    constexpr uint32_t A_BYTES = BM * BK * 2, WK_BYTES = BNW * BK * 2, W_MAX = 4 * WK_BYTES;      // resident weights: up to 4 k-blocks of 32 KB
+    const uint32_t ring = sbase + W_MAX;
+    const uint32_t bar0 = ring + kStagesWS * A_BYTES;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (kStagesWS + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * kStagesWS + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * kStagesWS + 2 + a); };
+    const uint32_t W_FULL = bar0 + 8u * (2 * kStagesWS + 4);
+    const uint32_t slot_off = W_MAX + kStagesWS * A_BYTES + 8 * (2 * kStagesWS + 5);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + slot_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t epi_stage = sbase + ((slot_off + 16 + 127) & ~127u) + (warp & 3) * kEpiStage;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesWS; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        mbar_init(W_FULL, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + slot_off), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const long long n_tiles = (M + BM - 1) / BM;
+    const int kblocks = K / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(W_FULL, kblocks * WK_BYTES);
+            for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sbase + kb * WK_BYTES, &tmW, kb * BK, 0, W_FULL);
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (int)tile * BM;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStagesWS, ph = (it / kStagesWS) & 1u;
+                    mbar_wait(EMPTY(s), ph ^ 1u);
+                    mbar_expect_tx(FULL(s), A_BYTES);
+                    tma_load_2d(ring + s * A_BYTES, &tmA, kb * BK, m0, FULL(s));
                 }
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            constexpr uint32_t idesc = idesc_f16(BM, BNW);
+            mbar_wait(W_FULL, 0);
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+                mbar_wait(ACC_EMPTY(acc), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BNW;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStagesWS, ph = (it / kStagesWS) & 1u;
+                    mbar_wait(FULL(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + s * A_BYTES, sw = sbase + kb * WK_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks)
+                        mma_ss(d, desc_sw128(sa + ks * 32), desc_sw128(sw + ks * 32), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    tc_commit(EMPTY(s));
+                }
+                tc_commit(ACC_FULL(acc));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tcount = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+            mbar_wait(ACC_FULL(acc), aph);
+            tc_fence_after();
+            epilogue_rows<BNW>(lane_base + acc * BNW, epi_stage, bias, C, ldc, tile * BM + q * 32, M, 0, relu, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
@@ -249,6 +373,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem_slot_addr = bar0 + 8u * (2 * kStages2 + 4);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kStages2 * STAGE + 8 * (2 * kStages2 + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t epi_stage = sbase + ((kStages2 * STAGE + 8 * (2 * kStages2 + 4) + 16 + 127) & ~127u) + (warp & 3) * kEpiStage;
     const uint32_t rank = cluster_ctarank();
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
@@ -314,28 +439,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
             const long long m0 = (tile / n_tiles_n) * (2 * BM) + (long long)rank * BM;
             const int n0 = (int)(tile % n_tiles_n) * BN2;
-            const long long row = m0 + q * 32 + lane;
             mbar_wait(ACC_FULL(acc), aph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN2 / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(lane_base + acc * BN2 + c * 32, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-                    uint4* dst = reinterpret_cast<uint4*>(C + row * ldc + n0 + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float x = __uint_as_float(r[8 * j + i]) + (bias ? __ldg(bias + n0 + c * 32 + 8 * j + i) : 0.f);
-                            v[i] = relu ? fmaxf(x, 0.f) : x;
-                        }
-                        dst[j] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    }
-                }
-            }
+            epilogue_rows<BN2>(lane_base + acc * BN2, epi_stage, bias, C, ldc, m0 + q * 32, M, n0, relu, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
@@ -393,10 +499,25 @@ static int launch(const __half* A, long long lda, const __half* W, long long ldw
     if (!n_sm_of[dev]) NEO_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = (int)(tiles < n_sm_of[dev] ? tiles : n_sm_of[dev]);
-    const size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * kStages + 4) + 16 + 1024;
+    const size_t smem = (((size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * kStages + 4) + 16 + 127) & ~(size_t)127) + 4 * kEpiStage + 1024;
     NEO_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_f16_kernel<BN><<<grid, kThreads, smem, s>>>(tmA, tmW, bias, C, M, N, K, ldc, relu);
     NEO_LAUNCH_CHECK("gemm_f16_kernel");
+    return NEO_OK;
+}
+
+static int launch_ws(const __half* A, long long lda, const __half* W, long long ldw, const float* bias, __half* C, long long ldc, long long M,
+                     int K, int relu, int n_sm, cudaStream_t s) {
+    alignas(64) CUtensorMap tmA, tmW;
+    int rc;
+    if ((rc = make_tmap_2d(&tmA, A, M, K, lda, BM))) return rc;
+    if ((rc = make_tmap_2d(&tmW, W, BNW, K, ldw, BNW))) return rc;
+    const long long tiles = (M + BM - 1) / BM;
+    const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    const size_t smem = (((size_t)4 * BNW * BK * 2 + (size_t)kStagesWS * BM * BK * 2 + 8 * (2 * kStagesWS + 5) + 16 + 127) & ~(size_t)127) + 4 * kEpiStage + 1024;
+    NEO_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_f16_ws_kernel<<<grid, kThreads, smem, s>>>(tmA, tmW, bias, C, M, K, ldc, relu);
+    NEO_LAUNCH_CHECK("gemm_f16_ws_kernel");
     return NEO_OK;
 }
 
@@ -409,7 +530,7 @@ static int launch_pair(const __half* A, long long lda, const __half* W, long lon
     const long long tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
     const long long pairs = n_sm / 2;
     const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
-    const size_t smem = (size_t)kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 8 * (2 * kStages2 + 4) + 16 + 1024;
+    const size_t smem = (((size_t)kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 8 * (2 * kStages2 + 4) + 16 + 127) & ~(size_t)127) + 4 * kEpiStage + 1024;
     NEO_CUDA(cudaFuncSetAttribute(gemm_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_f16_pair_kernel<<<grid, kThreads, smem, s>>>(tmA, tmW, bias, C, M, N, K, ldc, relu);
     NEO_LAUNCH_CHECK("gemm_f16_pair_kernel");
@@ -431,14 +552,18 @@ int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const f
     __half* c = (__half*)C;
     if (N % 256 == 0) {
         // CTA pairs (256 x 256 tiles) once there is a tile for every pair of SMs; NEO_GEMM_PAIR=0 keeps the single-CTA kernel (A/B runs)
-        static int use_pair = -1, n_sm = 0;
+        static int use_pair = -1, use_ws = 1, n_sm = 0;
         if (use_pair < 0) {
             const char* e = getenv("NEO_GEMM_PAIR");
+            const char* e2 = getenv("NEO_GEMM_WS");
+            use_ws = !(e2 && e2[0] == '0');
             use_pair = !(e && e[0] == '0');
             int dev = 0;
             NEO_CUDA(cudaGetDevice(&dev));
             NEO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
+        // 256-wide layer with a weight matrix that fits shared memory and at least one row tile per SM: weight-stationary kernel
+        if (use_ws && N == 256 && K <= 256 && (M + BM - 1) / BM >= n_sm) return launch_ws(a, lda, w, ldw, bias, c, ldc, M, K, relu, n_sm, s);
         const long long tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * (N / 256);
         if (use_pair && tiles2 >= n_sm / 2) return launch_pair(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, n_sm, s);
         return launch<256>(a, lda, w, ldw, bias, c, ldc, M, N, K, relu, s);

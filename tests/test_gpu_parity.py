@@ -717,11 +717,12 @@ def test_output_side_psnr_and_frames(cuda, tmp_path):
 
 
 @pytest.mark.parametrize("M,N,K,relu", [(1000, 1024, 512, 1), (257, 256, 1536, 1), (4096, 128, 320, 1), (130, 64, 64, 0), (70000, 1024, 1024, 1),
-                                          (20001, 256, 128, 0), (19000, 512, 1536, 1)])
+                                          (20001, 256, 128, 0), (19000, 512, 1536, 1), (40000, 256, 256, 1), (19000, 256, 64, 1)])
 def test_tc_dense_vs_torch(cuda, M, N, K, relu):
     """The tensor-core dense layer of the wide MLPs (csrc/gemm_tc.cu: TMA tile loads + tcgen05, fp16 operands, fp32 accumulate) against a
-    plain PyTorch fp32 reference of the same op on the fp16-rounded operands; ragged M, every N tile width (64/128/256), K up to 1536; the
-    last three shapes have a 256 x 256 tile for every SM pair and run the cta_group::2 kernel (gemm_f16_pair_kernel).
+    plain PyTorch fp32 reference of the same op on the fp16-rounded operands; ragged M, every N tile width (64/128/256), K up to 1536; 
+    (70000,1024,1024) and (19000,512,1536) have a 256 x 256 tile for every SM pair and run the cta_group::2 kernel (gemm_f16_pair_kernel);
+    the N = 256, K <= 256 shapes with a row tile for every SM run the weight-stationary kernel (gemm_f16_ws_kernel).
     Stated: |err| <= 2e-3 * max|ref| (fp32 accumulation order + the fp16 rounding of the output)."""
     from neo360_b200 import _lib as L
     lib = L.load()
