@@ -552,16 +552,19 @@ int gemm_f16(const void* A, long long lda, const void* W, long long ldw, const f
     __half* c = (__half*)C;
     if (N % 256 == 0) {
         // CTA pairs (256 x 256 tiles) once there is a tile for every pair of SMs; NEO_GEMM_PAIR=0 keeps the single-CTA kernel (A/B runs)
-        static int use_pair = -1, use_ws = 1, n_sm = 0;
+        static int use_pair = -1, use_ws = 1;
+        static int n_sm_of[64] = {0};              // per device: a process may drive several GPUs
         if (use_pair < 0) {
             const char* e = getenv("NEO_GEMM_PAIR");
             const char* e2 = getenv("NEO_GEMM_WS");
             use_ws = !(e2 && e2[0] == '0');
             use_pair = !(e && e[0] == '0');
-            int dev = 0;
-            NEO_CUDA(cudaGetDevice(&dev));
-            NEO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
+        int dev = 0;
+        NEO_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return NEO_ERR_UNSUPPORTED; }
+        if (!n_sm_of[dev]) NEO_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        const int n_sm = n_sm_of[dev];
         // 256-wide layer with a weight matrix that fits shared memory and at least one row tile per SM: weight-stationary kernel
         if (use_ws && N == 256 && K <= 256 && (M + BM - 1) / BM >= n_sm) return launch_ws(a, lda, w, ldw, bias, c, ldc, M, K, relu, n_sm, s);
         const long long tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * (N / 256);

@@ -412,33 +412,61 @@ __global__ void composite_kernel(const float* __restrict__ raw_density, const fl
     }
 }
 
-// ---- tensor-core path helpers: out[m][c] = sum_k fp16 h[m][k] * w[c][k] + b[c]  for tiny N (density: 1, rgb: 3); one warp per row ----
-__global__ void rowdot_f16_kernel(const __half* __restrict__ H, long long ld, int K, const float* __restrict__ Wt, const float* __restrict__ b,
-                                  int N, long long M, float* __restrict__ out) {
-    const long long m = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (m >= M) return;
-    const __half* h = H + m * ld;
-    for (int c = 0; c < N; ++c) {
-        float acc = 0.f;
-        for (int k = lane * 8; k < K; k += 256) {
-            const uint4 v = *reinterpret_cast<const uint4*>(h + k);
-            const __half2* hv = reinterpret_cast<const __half2*>(&v);
+// ---- tensor-core path helpers: out[m][c] = sum_k fp16 h[m][k] * w[c][k] + b[c]  for tiny N (density: 1, rgb: 3) ----
+// HBM-bound (one pass over the activation rows).  8 lanes per row, 4 rows per warp: every load instruction fetches four whole
+// 128-byte lines; the weights sit in shared memory (fp32, read as broadcast float4); 3 shuffles finish a row.
+constexpr int kRowdotIters = 4;          // row groups per warp: 8 warps x 4 rows x 4 = 128 rows per block
+template <int N>
+__global__ void __launch_bounds__(256) rowdot_f16_kernel(const __half* __restrict__ H, long long ld, int K, const float* __restrict__ Wt,
+                                                         const float* __restrict__ b, long long M, float* __restrict__ out) {
+    extern __shared__ __align__(16) float wsm[];          // [N][K]
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) wsm[i] = Wt[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & 7, rsel = lane >> 3, warp = threadIdx.x >> 5;
+    float bias[N];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(hv[i]);
-                acc = fmaf(f.x, __ldg(Wt + (size_t)c * K + k + 2 * i), acc);
-                acc = fmaf(f.y, __ldg(Wt + (size_t)c * K + k + 2 * i + 1), acc);
+    for (int c = 0; c < N; ++c) bias[c] = b[c];
+#pragma unroll 1
+    for (int it = 0; it < kRowdotIters; ++it) {
+        const long long m = (((long long)blockIdx.x * kRowdotIters + it) * 8 + warp) * 4 + rsel;
+        float acc[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[c] = 0.f;
+        if (m < M) {
+            const __half* h = H + m * ld;
+            for (int k = sub * 8; k < K; k += 64) {
+                const uint4 v = *reinterpret_cast<const uint4*>(h + k);
+                const __half2* hv = reinterpret_cast<const __half2*>(&v);
+                const float2 f0 = __half22float2(hv[0]), f1 = __half22float2(hv[1]), f2 = __half22float2(hv[2]), f3 = __half22float2(hv[3]);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + c * K + k), w1 = *reinterpret_cast<const float4*>(wsm + c * K + k + 4);
+                    acc[c] = fmaf(f0.x, w0.x, fmaf(f0.y, w0.y, fmaf(f1.x, w0.z, fmaf(f1.y, w0.w,
+                             fmaf(f2.x, w1.x, fmaf(f2.y, w1.y, fmaf(f3.x, w1.z, fmaf(f3.y, w1.w, acc[c]))))))));
+                }
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[m * N + c] = acc + b[c];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+            acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+        }
+        if (m < M && sub == 0) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) out[m * N + c] = acc[c] + bias[c];
+        }
     }
 }
 
 }  // namespace mip
 int launch_rowdot_f16(const void* H, long long ld, int K, const float* W, const float* b, int N, long long M, float* out, cudaStream_t s) {
-    mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>((const __half*)H, ld, K, W, b, N, M, out);
+    if (M <= 0) return NEO_OK;
+    if ((K % 8) || (ld % 8) || (N != 1 && N != 3)) { set_error("rowdot_f16: K %% 8, ld %% 8 and N in {1, 3} required (K=%d ld=%lld N=%d)", K, ld, N); return NEO_ERR_INVALID; }
+    const unsigned grid = (unsigned)((M + 8 * 4 * mip::kRowdotIters - 1) / (8 * 4 * mip::kRowdotIters));
+    const size_t smem = (size_t)N * K * sizeof(float);
+    if (N == 1) mip::rowdot_f16_kernel<1><<<grid, 256, smem, s>>>((const __half*)H, ld, K, W, b, M, out);
+    else mip::rowdot_f16_kernel<3><<<grid, 256, smem, s>>>((const __half*)H, ld, K, W, b, M, out);
     NEO_LAUNCH_CHECK("rowdot_f16_kernel");
     return NEO_OK;
 }
@@ -530,8 +558,7 @@ int mlp_tc(const NeoMipMLPParams& p, const WSM& w, long long M, int n, const flo
         if ((rc = gemm_f16(buf[(l - 1) & 1], ld, wl, K, p.b[l], buf[l & 1], ld, M, W, K, 1, s))) return rc;
     }
     const __half* h = buf[(p.depth - 1) & 1];
-    mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h, ld, W, p.wsig, p.bsig, 1, M, rawd);
-    NEO_LAUNCH_CHECK("mip rowdot_f16_kernel(density)");
+    if ((rc = launch_rowdot_f16(h, ld, W, p.wsig, p.bsig, 1, M, rawd, s))) return rc;
     if (p.wrgb) {
         __half* B = (__half*)w.B16;
         __half* V = (__half*)w.V16;
@@ -546,8 +573,7 @@ int mlp_tc(const NeoMipMLPParams& p, const WSM& w, long long M, int n, const flo
         if ((rc = f32_to_f16_pad(p.wv0, 128, 256, 256 + 27, wv, 256, ldb, s))) return rc;
         if ((rc = f32_to_f16_pad(p.wv0 + 256, 128, 27, 256 + 27, wv + 256, kDirPad, ldb, s))) return rc;
         if ((rc = gemm_f16(B, ldb, wv, ldb, p.bv0, V, 128, M, 128, ldb, 1, s))) return rc;
-        mip::rowdot_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(V, 128, 128, p.wrgb, p.brgb, 3, M, rawc);
-        NEO_LAUNCH_CHECK("mip rowdot_f16_kernel(rgb)");
+        if ((rc = launch_rowdot_f16(V, 128, 128, p.wrgb, p.brgb, 3, M, rawc, s))) return rc;
     }
     return NEO_OK;
 }
