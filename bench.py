@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--train-matmul", choices=("fp32", "tf32"), default="fp32",
                     help="train mode: precision of the framework GEMMs of the dense layers.  tf32 = torch.backends.cuda.matmul.allow_tf32, the setting "
                          "the reference was trained under (torch 1.11 default, SURVEY.md 8(d))")
+    ap.add_argument("--train-formulation", choices=("projected", "reference"), default="projected",
+                    help="train mode: projected = map columns of layers 0/3 applied to the feature maps once per step (exact re-association, default); "
+                         "reference = the reference's row-by-row K=703/831 input layers")
     ap.add_argument("--freeze-encoder", action="store_true", help="train mode: MLPs only (finetune mode); default trains GridEncoder inside the step")
     return ap.parse_args()
 

@@ -79,7 +79,8 @@ typedef struct NeoScene NeoScene;
 
 /* Build the per-scene state: channel-last feature maps, R^T / -R^T t per view, MLP weights packed for
  * the selected precision.  mlps[4] = {fg_coarse, bg_coarse, fg_fine, bg_fine} (model.py:215-237).
- * `precision_mask` is a bit-or of (1<<NEO_PREC_FP32) | (1<<NEO_PREC_TC): which paths to prepare. */
+ * `precision_mask` is a bit-or of (1<<NEO_PREC_FP32) | (1<<NEO_PREC_TC): which paths to prepare; 0 = cameras and grid geometry only
+ * (enough for neo_index_maps / neo_index_maps_bwd; rendering such a scene returns NEO_ERR_INVALID). */
 int neo_scene_create(const NeoSceneDesc* desc, const NeoMLPParams mlps[4], int precision_mask,
                      NeoScene** out, void* stream);
 void neo_scene_free(NeoScene* scene);
@@ -180,6 +181,15 @@ int neo_sample_pdf(const float* rays_o, const float* rays_d, const float* far, c
 int neo_volumetric_rendering(const float* rgb, const float* sigma, const float* t_vals, const float* rays_d,
                              const float* far, int n_rays, int N, int white_bkgd, int in_sphere, float* comp_rgb,
                              float* acc, float* weights, float* bg_lambda, float* depth, void* stream);
+/* The same two lookups over CALLER-OWNED channel-last maps (nv,H,W,C) fp32 of any channel count C % 4 == 0, with the scene's cameras and
+ * grid geometry (spatial sizes = the scene's latent / plane sizes).  Used by the training path, which looks up maps projected through the
+ * current first / skip layer weights (linearity of encoder_tp_fusion_conv.py:122-209 and encoder_pn.py:101-152).  latent_cl or the three
+ * planes may be NULL (then that output is skipped).  out_local / out_world: (nv*M, C), rows ordered (view, point). */
+int neo_index_maps(const NeoScene* scene, const float* pts, int M, int C, const float* latent_cl, const float* xz_cl, const float* xy_cl,
+                   const float* yz_cl, float* out_local, float* out_world, void* stream);
+/* Backward of neo_index_maps: scatter-add of the row gradients (nv*M, C) into zero-initialised channel-last gradient maps. */
+int neo_index_maps_bwd(const NeoScene* scene, const float* pts, int M, int C, const float* g_local, const float* g_world,
+                       float* g_latent_cl, float* g_xz_cl, float* g_xy_cl, float* g_yz_cl, void* stream);
 /* encoder_tp_fusion_conv.py:122-209: pts (M,3) world -> (nv*M,128), rows ordered (view, point). */
 int neo_index_grid(const NeoScene* scene, const float* pts, int M, float* out, void* stream);
 /* model.py:239-264 (get_local_feats): pts (M,3) world -> (nv*M,512). */

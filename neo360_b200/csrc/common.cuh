@@ -230,6 +230,10 @@ int launch_field_fp32(const NeoScene* sc, const NeoRays* rays, const float* far,
                       float* rgb, float* sigma, cudaStream_t s);
 int launch_index_grid(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s);
 int launch_index_local(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s);
+int launch_index_maps(const NeoScene* sc, const float* pts, int M, int C, const float* lat, const float* xz, const float* xy, const float* yz,
+                      float* out_local, float* out_world, cudaStream_t s);
+int launch_index_maps_bwd(const NeoScene* sc, const float* pts, int M, int C, const float* g_local, const float* g_world, float* g_lat, float* g_xz,
+                          float* g_xy, float* g_yz, cudaStream_t s);
 int launch_index_bwd(const NeoScene* sc, const float* pts, int M, int local, const float* g_out, float* g_lat, float* g_xz, float* g_xy,
                      float* g_yz, cudaStream_t s);
 // field_tc.cu

@@ -299,36 +299,41 @@ int launch_field_fp32(const NeoScene* sc, const NeoRays* rays, const float* far,
 // ------------------------------------------------------------------------------------------------
 // stage-level lookups (index_grid / get_local_feats): rows ordered (view, point), channels contiguous
 // ------------------------------------------------------------------------------------------------
-__global__ void index_kernel(SceneDev sc, const float* __restrict__ pts, int M, int local, float* __restrict__ out) {
-    int C = local ? kLocalCh : kWorldCh;
+// Maps are passed explicitly (channel-last (nv, H, W, C), spatial sizes = the scene's): the scene's own raw maps for index_grid /
+// get_local_feats, or caller-owned maps of any channel count C % 4 == 0 for the training path's projected maps (neo_index_maps*).
+struct MapSet { const float* lat; const float* pl[3]; };
+struct MapSetW { float* lat; float* pl[3]; };
+
+__global__ void index_kernel(SceneDev sc, const float* __restrict__ pts, int M, int local, int C, MapSet maps, float* __restrict__ out) {
     long long row = blockIdx.x;           // v*M + m
     int v = (int)(row / M), m = (int)(row % M);
     float c[3];
     to_camera(sc.views[v], pts + 3 * (size_t)m, c);
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-        float val;
-        if (local) {
-            float gx, gy;
-            Taps t;
-            local_grid_coords(sc, c, gx, gy);
-            bilinear_taps(gx, gy, sc.lat_w, sc.lat_h, t);
-            const float* lat = sc.latent_cl + (size_t)v * sc.lat_h * sc.lat_w * kLocalCh;
-            val = 0.f;
-            for (int tp = 0; tp < 4; ++tp) val += __ldg(lat + (size_t)t.idx[tp] * kLocalCh + ch) * t.w[tp];
-        } else {
+    if (local) {
+        float gx, gy;
+        Taps t;
+        local_grid_coords(sc, c, gx, gy);
+        bilinear_taps(gx, gy, sc.lat_w, sc.lat_h, t);
+        const float* lat = maps.lat + (size_t)v * sc.lat_h * sc.lat_w * C;
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+            float val = 0.f;
+            for (int tp = 0; tp < 4; ++tp) val += __ldg(lat + (size_t)t.idx[tp] * C + ch) * t.w[tp];
+            out[row * C + ch] = val;
+        }
+    } else {
+        const float ga[3] = {c[0], c[0], c[1]}, gb[3] = {c[2], c[1], c[2]};
+        Taps t[3];
+        for (int pi = 0; pi < 3; ++pi) bilinear_taps(ga[pi], gb[pi], sc.plane_w, sc.plane_h, t[pi]);
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
             float pl[3];
-            const float ga[3] = {c[0], c[0], c[1]}, gb[3] = {c[2], c[1], c[2]};
             for (int pi = 0; pi < 3; ++pi) {
-                Taps t;
-                bilinear_taps(ga[pi], gb[pi], sc.plane_w, sc.plane_h, t);
-                const float* pp = sc.planes_cl[pi] + (size_t)v * sc.plane_h * sc.plane_w * kWorldCh;
+                const float* pp = maps.pl[pi] + (size_t)v * sc.plane_h * sc.plane_w * C;
                 float a = 0.f;
-                for (int tp = 0; tp < 4; ++tp) a += __ldg(pp + (size_t)t.idx[tp] * kWorldCh + ch) * t.w[tp];
+                for (int tp = 0; tp < 4; ++tp) a += __ldg(pp + (size_t)t[pi].idx[tp] * C + ch) * t[pi].w[tp];
                 pl[pi] = a;
             }
-            val = (pl[0] + pl[1]) + pl[2];
+            out[row * C + ch] = (pl[0] + pl[1]) + pl[2];
         }
-        out[row * C + ch] = val;
     }
 }
 
@@ -338,9 +343,7 @@ __global__ void index_kernel(SceneDev sc, const float* __restrict__ pts, int M, 
 // (nv, H, W, C): d map[v][tap texel][:] += w_tap * d out[row][:].  A row's channels are contiguous in both tensors, so the
 // atomics of one warp are 16-byte vector reductions on consecutive addresses (red.global.add.v4.f32).
 // ------------------------------------------------------------------------------------------------
-__global__ void index_bwd_kernel(SceneDev sc, const float* __restrict__ pts, int M, int local, const float* __restrict__ g_out,
-                                 float* __restrict__ g_lat, float* __restrict__ g_xz, float* __restrict__ g_xy, float* __restrict__ g_yz) {
-    const int C = local ? kLocalCh : kWorldCh;
+__global__ void index_bwd_kernel(SceneDev sc, const float* __restrict__ pts, int M, int local, int C, const float* __restrict__ g_out, MapSetW maps) {
     const long long row = blockIdx.x;           // v*M + m
     const int v = (int)(row / M), m = (int)(row % M);
     float c[3];
@@ -351,26 +354,25 @@ __global__ void index_bwd_kernel(SceneDev sc, const float* __restrict__ pts, int
         Taps t;
         local_grid_coords(sc, c, gx, gy);
         bilinear_taps(gx, gy, sc.lat_w, sc.lat_h, t);
-        float* base = g_lat + (size_t)v * sc.lat_h * sc.lat_w * kLocalCh;
+        float* base = maps.lat + (size_t)v * sc.lat_h * sc.lat_w * C;
         for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
             const float4 gv = g[q];
             for (int tp = 0; tp < 4; ++tp) {
                 const float w = t.w[tp];
-                if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * kLocalCh) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
+                if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * C) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
             }
         }
     } else {
         const float ga[3] = {c[0], c[0], c[1]}, gb[3] = {c[2], c[1], c[2]};
-        float* maps[3] = {g_xz, g_xy, g_yz};
         for (int pi = 0; pi < 3; ++pi) {
             Taps t;
             bilinear_taps(ga[pi], gb[pi], sc.plane_w, sc.plane_h, t);
-            float* base = maps[pi] + (size_t)v * sc.plane_h * sc.plane_w * kWorldCh;
+            float* base = maps.pl[pi] + (size_t)v * sc.plane_h * sc.plane_w * C;
             for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
                 const float4 gv = g[q];
                 for (int tp = 0; tp < 4; ++tp) {
                     const float w = t.w[tp];
-                    if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * kWorldCh) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
+                    if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.idx[tp] * C) + q, make_float4(gv.x * w, gv.y * w, gv.z * w, gv.w * w));
                 }
             }
         }
@@ -379,19 +381,38 @@ __global__ void index_bwd_kernel(SceneDev sc, const float* __restrict__ pts, int
 
 int launch_index_bwd(const NeoScene* sc, const float* pts, int M, int local, const float* g_out, float* g_lat, float* g_xz, float* g_xy,
                      float* g_yz, cudaStream_t s) {
-    index_bwd_kernel<<<(unsigned)((long long)sc->dev.nv * M), local ? 128 : 32, 0, s>>>(sc->dev, pts, M, local, g_out, g_lat, g_xz, g_xy, g_yz);
+    const int C = local ? kLocalCh : kWorldCh;
+    index_bwd_kernel<<<(unsigned)((long long)sc->dev.nv * M), local ? 128 : 32, 0, s>>>(sc->dev, pts, M, local, C, g_out, MapSetW{g_lat, {g_xz, g_xy, g_yz}});
     NEO_LAUNCH_CHECK("index_bwd_kernel");
     return NEO_OK;
 }
 
 int launch_index_grid(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s) {
-    index_kernel<<<(unsigned)((long long)sc->dev.nv * M), 128, 0, s>>>(sc->dev, pts, M, 0, out);
+    index_kernel<<<(unsigned)((long long)sc->dev.nv * M), 128, 0, s>>>(sc->dev, pts, M, 0, kWorldCh,
+                                                                        MapSet{nullptr, {sc->dev.planes_cl[0], sc->dev.planes_cl[1], sc->dev.planes_cl[2]}}, out);
     NEO_LAUNCH_CHECK("index_kernel(grid)");
     return NEO_OK;
 }
 int launch_index_local(const NeoScene* sc, const float* pts, int M, float* out, cudaStream_t s) {
-    index_kernel<<<(unsigned)((long long)sc->dev.nv * M), 128, 0, s>>>(sc->dev, pts, M, 1, out);
+    index_kernel<<<(unsigned)((long long)sc->dev.nv * M), 128, 0, s>>>(sc->dev, pts, M, 1, kLocalCh, MapSet{sc->dev.latent_cl, {nullptr, nullptr, nullptr}}, out);
     NEO_LAUNCH_CHECK("index_kernel(local)");
+    return NEO_OK;
+}
+// caller-owned maps (training on projected maps): lookups and their scatter-add backward with the scene's cameras / grid geometry
+int launch_index_maps(const NeoScene* sc, const float* pts, int M, int C, const float* lat, const float* xz, const float* xy, const float* yz,
+                      float* out_local, float* out_world, cudaStream_t s) {
+    const unsigned grid = (unsigned)((long long)sc->dev.nv * M);
+    const int threads = C >= 128 ? 128 : 64;
+    if (lat) { index_kernel<<<grid, threads, 0, s>>>(sc->dev, pts, M, 1, C, MapSet{lat, {nullptr, nullptr, nullptr}}, out_local); NEO_LAUNCH_CHECK("index_kernel(maps, local)"); }
+    if (xz) { index_kernel<<<grid, threads, 0, s>>>(sc->dev, pts, M, 0, C, MapSet{nullptr, {xz, xy, yz}}, out_world); NEO_LAUNCH_CHECK("index_kernel(maps, world)"); }
+    return NEO_OK;
+}
+int launch_index_maps_bwd(const NeoScene* sc, const float* pts, int M, int C, const float* g_local, const float* g_world, float* g_lat, float* g_xz,
+                          float* g_xy, float* g_yz, cudaStream_t s) {
+    const unsigned grid = (unsigned)((long long)sc->dev.nv * M);
+    const int threads = C / 4 >= 64 ? 64 : 32;
+    if (g_local) { index_bwd_kernel<<<grid, threads, 0, s>>>(sc->dev, pts, M, 1, C, g_local, MapSetW{g_lat, {nullptr, nullptr, nullptr}}); NEO_LAUNCH_CHECK("index_bwd_kernel(maps, local)"); }
+    if (g_world) { index_bwd_kernel<<<grid, threads, 0, s>>>(sc->dev, pts, M, 0, C, g_world, MapSetW{nullptr, {g_xz, g_xy, g_yz}}); NEO_LAUNCH_CHECK("index_bwd_kernel(maps, world)"); }
     return NEO_OK;
 }
 

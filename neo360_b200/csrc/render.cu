@@ -219,6 +219,22 @@ extern "C" int neo_index_local_bwd(const NeoScene* sc, const float* pts, int M, 
     if (!sc || M <= 0 || !pts || !g_out || !g_latent) { set_error("neo_index_local_bwd: bad arguments"); return NEO_ERR_INVALID; }
     return launch_index_bwd(sc, pts, M, 1, g_out, g_latent, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
+extern "C" int neo_index_maps(const NeoScene* sc, const float* pts, int M, int C, const float* latent_cl, const float* xz_cl, const float* xy_cl,
+                              const float* yz_cl, float* out_local, float* out_world, void* stream) {
+    if (!sc || M <= 0 || !pts || C < 4 || (C % 4) || (latent_cl && !out_local) || (xz_cl && !(xy_cl && yz_cl && out_world)) || !(latent_cl || xz_cl)) {
+        set_error("neo_index_maps: bad arguments (C %% 4 == 0, a latent map and/or all three planes, outputs for what is given)");
+        return NEO_ERR_INVALID;
+    }
+    return launch_index_maps(sc, pts, M, C, latent_cl, xz_cl, xy_cl, yz_cl, out_local, out_world, (cudaStream_t)stream);
+}
+extern "C" int neo_index_maps_bwd(const NeoScene* sc, const float* pts, int M, int C, const float* g_local, const float* g_world, float* g_latent_cl,
+                                  float* g_xz_cl, float* g_xy_cl, float* g_yz_cl, void* stream) {
+    if (!sc || M <= 0 || !pts || C < 4 || (C % 4) || (g_local && !g_latent_cl) || (g_world && !(g_xz_cl && g_xy_cl && g_yz_cl)) || !(g_local || g_world)) {
+        set_error("neo_index_maps_bwd: bad arguments");
+        return NEO_ERR_INVALID;
+    }
+    return launch_index_maps_bwd(sc, pts, M, C, g_local, g_world, g_latent_cl, g_xz_cl, g_xy_cl, g_yz_cl, (cudaStream_t)stream);
+}
 extern "C" int neo_index_grid(const NeoScene* sc, const float* pts, int M, float* out, void* stream) {
     if (!sc || M <= 0 || !sc->dev.planes_cl[0]) { set_error("neo_index_grid: needs a scene prepared with NEO_PREC_FP32"); return NEO_ERR_INVALID; }
     return launch_index_grid(sc, pts, M, out, (cudaStream_t)stream);

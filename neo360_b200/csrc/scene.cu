@@ -185,10 +185,11 @@ extern "C" int neo_scene_create(const NeoSceneDesc* d, const NeoMLPParams mlps[4
         set_error("neo_scene_create: null feature map / camera pointer");
         return NEO_ERR_INVALID;
     }
-    if (!(precision_mask & ((1 << NEO_PREC_FP32) | (1 << NEO_PREC_TC)))) {
-        set_error("neo_scene_create: empty precision mask");
+    if (precision_mask & ~((1 << NEO_PREC_FP32) | (1 << NEO_PREC_TC))) {
+        set_error("neo_scene_create: unknown bits in the precision mask (%d)", precision_mask);
         return NEO_ERR_INVALID;
     }
+    // precision_mask == 0: cameras and grid geometry only (neo_index_maps* of the training path); rendering such a scene is an error
     cudaStream_t s = (cudaStream_t)stream;
     NeoScene* sc = new NeoScene();
     sc->desc = *d;

@@ -150,7 +150,7 @@ class NeRF_TP(nn.Module):
         d.latent = L.ptr(f(latent))
         d.src_poses, d.src_focal, d.src_c = L.ptr(f(src_poses)), L.ptr(f(src_focal)), L.ptr(f(src_c))
         arr = (L.NeoMLPParams * 4)(*[m.to(dev).c_params(keep) for m in self._mlps()])
-        precisions = precisions or [self.precision]
+        precisions = [self.precision] if precisions is None else precisions      # [] = cameras / geometry only (projected-map training)
         mask = 0
         for p in precisions:
             mask |= 1 << PRECISIONS[p]
@@ -292,7 +292,9 @@ class NeRF_TP(nn.Module):
             maps, cams, wh = list(a[:4]), list(a[4:7]), a[7]
         else:
             raise RuntimeError("no scene: call set_scene(...) or pass planes_*/latent in `rays`, or give an encoder")
-        self.set_scene(*maps, *cams, wh, precisions=["fp32"])          # the lookups read the scene's channel-last copies of THESE maps
+        # reference formulation: the lookups read the scene's channel-last copies of THESE maps; projected formulation (default): the
+        # scene only carries the cameras and grid geometry, the maps are projected under autograd in training.render_train
+        self.set_scene(*maps, *cams, wh, precisions=[] if getattr(self, "train_projected", True) else ["fp32"])
         r = dict(rays)
         r["src_poses"] = cams[0]
         return training.render_train(self, r, maps[:3], maps[3], randomized, white_bkgd, out_depth, uniforms=rays.get("_uniforms"))

@@ -8,8 +8,13 @@ What runs where
     `neo_index_grid_bwd|local_bwd`: 16-byte vector reductions into channel-last gradient maps), alpha compositing (forward
     `neo_volumetric_rendering`, backward `neo_volumetric_rendering_bwd`);
   * host framework (autograd + plain library GEMMs): the dense layers of NeRFPPMLP, activations, positional encodings, losses and the
-    optimiser.  The tensor-core inference kernel (csrc/field_tc.cu) re-associates the network per scene (pre-projected maps), which
-    does not survive a weight update per step -- training keeps the reference formulation.
+    optimiser.
+  * formulation: by default (`net.train_projected`, True) the training step uses the same exact re-association as the tensor-core
+    inference kernel -- the lookups are linear, so the latent / tri-plane columns of layers 0 and 3 are applied to the feature MAPS once per
+    step (`P = F . [W0_map ; W3_map]^T`, 0.4 M texels) instead of to every looked-up row (7.9 M point-views): the K = 703 / 831 input
+    layers shrink to K = 63|84 and the lookups fetch 2 x 256 projected channels (`neo_index_maps`, backward `neo_index_maps_bwd`).  Autograd
+    differentiates through the projection, so the map-column weights and the encoder outputs get exactly the reference's gradients (to
+    fp32 re-association).  `train_projected = False` keeps the reference formulation row by row.
   * NCCL: ONE all-reduce over the flat gradient slab of the four MLPs per step (`allreduce_flat`), as the reference's DDP does.
 There is no CPU fallback: every op raises on CPU tensors.
 """
@@ -67,6 +72,40 @@ class _Lookup(torch.autograd.Function):
             L.check(lib.neo_index_local_bwd(sc.handle, L.ptr(p), M, L.ptr(g_local.contiguous().float()), L.ptr(g_lat), _stream()))
         nchw = lambda t: t.permute(0, 3, 1, 2)
         return None, nchw(g_planes[0]), nchw(g_planes[1]), nchw(g_planes[2]), nchw(g_lat), None
+
+
+class _LookupMaps(torch.autograd.Function):
+    """The two lookups over caller-owned channel-last maps of C channels (projected maps): lat_cl (NV,Hl,Wl,C), three planes
+    (NV,Hp,Wp,C) -> local (NV*M,C), world (NV*M,C); gradients are scatter-added into channel-last gradient maps."""
+
+    @staticmethod
+    def forward(ctx, pts, lat_cl, xz_cl, xy_cl, yz_cl, net):
+        lib = L.load()
+        p = pts.detach().reshape(-1, 3).contiguous().float()
+        sc = net._scene
+        M, nv, Cc = p.shape[0], sc.nv, lat_cl.shape[-1]
+        maps = [t.detach().contiguous().float() for t in (lat_cl, xz_cl, xy_cl, yz_cl)]
+        local = torch.empty(nv * M, Cc, device=p.device)
+        world = torch.empty(nv * M, Cc, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(lib.neo_index_maps(sc.handle, L.ptr(p), M, Cc, *[L.ptr(t) for t in maps], L.ptr(local), L.ptr(world), _stream()))
+        ctx.save_for_backward(p)
+        ctx.scene, ctx.C = sc, Cc
+        ctx.shapes = (lat_cl.shape, xz_cl.shape)
+        return local, world
+
+    @staticmethod
+    def backward(ctx, g_local, g_world):
+        lib = L.load()
+        (p,) = ctx.saved_tensors
+        sc, Cc = ctx.scene, ctx.C
+        M = p.shape[0]
+        g_lat = torch.zeros(ctx.shapes[0], device=p.device)
+        g_pl = [torch.zeros(ctx.shapes[1], device=p.device) for _ in range(3)]
+        with torch.cuda.device(p.device):
+            L.check(lib.neo_index_maps_bwd(sc.handle, L.ptr(p), M, Cc, L.ptr(g_local.contiguous().float()), L.ptr(g_world.contiguous().float()),
+                                           L.ptr(g_lat), L.ptr(g_pl[0]), L.ptr(g_pl[1]), L.ptr(g_pl[2]), _stream()))
+        return None, g_lat, g_pl[0], g_pl[1], g_pl[2], None
 
 
 class _Composite(torch.autograd.Function):
@@ -143,6 +182,33 @@ def _mlp(mlp, enc: Tensor, dir_tile: Tensor, world: Tensor, local: Tensor, nv: i
     return lin(mlp.rgb_layer, q), raw_sigma
 
 
+def _project_maps(mlp, enc_dim: int, latent_cl: Tensor, planes_cl: List[Tensor]):
+    """[P0 | P3] = F . [W0_map ; W3_map]^T per map: the latent (512) / tri-plane (128) columns of layers 0 and 3 applied to the channel-last
+    feature maps (model.py:110-158: x = [enc | local 512 | world 128], layer 3 sees [h 128 | x])."""
+    w0, w3 = mlp.pts_linears[0].weight, mlp.pts_linears[3].weight
+    wl = torch.cat([w0[:, enc_dim:enc_dim + 512], w3[:, 128 + enc_dim:128 + enc_dim + 512]], 0)       # (256, 512)
+    ww = torch.cat([w0[:, enc_dim + 512:], w3[:, 128 + enc_dim + 512:]], 0)                              # (256, 128)
+    return latent_cl @ wl.t(), [pc @ ww.t() for pc in planes_cl]
+
+
+def _mlp_projected(mlp, enc: Tensor, dir_tile: Tensor, local_p: Tensor, world_p: Tensor, nv: int):
+    """NeRFPPMLP.forward with the map columns of layers 0 / 3 already applied: local_p, world_p (NV*M, 256) = looked-up [P0 | P3]."""
+    M, E = enc.shape[1], enc.shape[-1]
+    lin = lambda m, x: F.linear(x, m.weight, m.bias)
+    e = enc.reshape(-1, E)
+    w0, w3 = mlp.pts_linears[0], mlp.pts_linears[3]
+    pm = local_p + world_p
+    h = torch.relu(F.linear(e, w0.weight[:, :E], w0.bias) + pm[:, :128])
+    h = torch.relu(lin(mlp.pts_linears[1], h))
+    h = torch.relu(lin(mlp.pts_linears[2], h))
+    h = torch.relu(F.linear(torch.cat([h, e], -1), w3.weight[:, :128 + E], w3.bias) + pm[:, 128:])
+    beta = lin(mlp.bottleneck_layer, h)
+    raw_sigma = lin(mlp.density_layer, h.reshape(nv, M, -1).mean(0))
+    q = lin(mlp.views_linear[0], torch.cat([beta, dir_tile], -1)).reshape(nv, M, -1).mean(0)
+    q = torch.relu(lin(mlp.views_linear[1], torch.relu(q)))
+    return lin(mlp.rgb_layer, q), raw_sigma
+
+
 def render_train(net, rays: Dict[str, Tensor], planes: List[Tensor], latent: Tensor, randomized: bool, white_bkgd: bool,
                  out_depth: bool = False, uniforms: Optional[List[Tensor]] = None):
     """NeRF_TP.forward (model.py:266-581, encoder hoisted) with autograd through the MLP parameters, `planes` (xz, xy, yz) and `latent`.
@@ -159,6 +225,10 @@ def render_train(net, rays: Dict[str, Tensor], planes: List[Tensor], latent: Ten
     denc = _pos_enc(dirs_cam, 0, 4)                                              # (NV,B,27)
     u = uniforms if uniforms is not None else [None] * 4
     mlps = net._mlps()                                                           # fg_coarse, bg_coarse, fg_fine, bg_fine
+    projected = getattr(net, "train_projected", True)
+    if projected:
+        latent_cl = latent.permute(0, 2, 3, 1)                                   # channel-last views: the projection contracts the last axis
+        planes_cl = [pl.permute(0, 2, 3, 1) for pl in planes]
     ret = []
     fg_t = bg_s = fg_w = bg_w = None
     for level in range(2):
@@ -175,8 +245,14 @@ def render_train(net, rays: Dict[str, Tensor], planes: List[Tensor], latent: Ten
             cam = _world2camera(enc_pts[..., :3].reshape(-1, 3), poses)          # (NV,B*N,3)
             if b == 1:
                 cam = torch.cat([cam, enc_pts[..., 3].reshape(1, -1, 1).repeat(nv, 1, 1)], -1)
-            world, local = _Lookup.apply(look_pts.reshape(-1, 3), planes[0], planes[1], planes[2], latent, net)
-            raw_rgb, raw_sigma = _mlp(mlps[2 * level + b], _pos_enc(cam, 0, 10), dir_tile, world, local, nv)
+            mlp = mlps[2 * level + b]
+            if projected:
+                pl_cl, pp_cl = _project_maps(mlp, 63 if b == 0 else 84, latent_cl, planes_cl)
+                local_p, world_p = _LookupMaps.apply(look_pts.reshape(-1, 3), pl_cl, pp_cl[0], pp_cl[1], pp_cl[2], net)
+                raw_rgb, raw_sigma = _mlp_projected(mlp, _pos_enc(cam, 0, 10), dir_tile, local_p, world_p, nv)
+            else:
+                world, local = _Lookup.apply(look_pts.reshape(-1, 3), planes[0], planes[1], planes[2], latent, net)
+                raw_rgb, raw_sigma = _mlp(mlp, _pos_enc(cam, 0, 10), dir_tile, world, local, nv)
             sigma = F.softplus(raw_sigma.reshape(B, N, 1) - 1.0)                 # model.py:392-393
             rgb = torch.sigmoid(raw_rgb.reshape(B, N, 3)) * (1 + 2 * 0.001) - 0.001
             wb = False if out_depth else white_bkgd                              # model.py:501,519 vs 551,560
@@ -242,6 +318,7 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
     sd.update(synth.make_mlp_params(0))
     net.load_state_dict(sd)
     net = net.to(dev).train()
+    net.train_projected = getattr(args, "train_formulation", "projected") == "projected"
     cams = [sc[k].to(dev) for k in ("src_poses", "src_focal", "src_c")]
     if with_encoder:
         # the reference's training step (models/neo360/model.py:697-820): the encoder runs inside the step and trains through the renderer
@@ -305,6 +382,9 @@ def bench_train(args, rank, world, local, dev, dist, pk, base, sampler, timed):
                                    else "frozen / absent: encoder outputs are leaf tensors (finetune mode, model.py:969-979)",
                         "batch": "pix_inds drawn on the host as the reference dataset does, rays + targets of the sampled pixels generated on the device "
                                  "from 20 resident target views (neo_sample_rays)",
+                        "formulation": "projected maps: [W0_map; W3_map] applied to the 0.4 M map texels once per step under autograd, lookups of 2x256 projected "
+                                       "channels, K=63|84 input layers (exact re-association)" if net.train_projected
+                                       else "reference: row-by-row K=703/831 input layers on the looked-up 640 raw channels",
                         "hand_written": "pixel sampling, ray sampling, lookups fwd/bwd, compositing fwd/bwd", "library": "dense layers and encoder (autograd), Adam"},
                 e2e={"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": 4},
                 final_loss=loss, clocks=sampler.result() if sampler else None)

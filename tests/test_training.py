@@ -97,12 +97,16 @@ def test_lookup_backward_vs_autograd(cuda):
 
 
 @pytest.mark.gpu
-def test_training_forward_and_gradients_vs_oracle(cuda):
+@pytest.mark.parametrize("projected", [True, False])
+def test_training_forward_and_gradients_vs_oracle(cuda, projected):
     """NeRF_TP.forward in training mode: the train tuples (model.py:577-579) equal the oracle's, and the gradients of
     MSE + distortion loss w.r.t. EVERY MLP parameter, the tri-planes and the latent equal autograd through the oracle (CPU, fp32).
-    Stated: tuples 2e-4; gradients within 5e-3 of each tensor's gradient scale (fp32 GEMM summation order, GPU vs CPU)."""
+    Both formulations: `projected` (default: map columns of layers 0 / 3 applied to the feature maps, lookups of the projected maps through
+    neo_index_maps / neo_index_maps_bwd) and the reference's row-by-row one.
+    Stated: tuples 2e-4; every gradient tensor within 1e-2 of its gradient scale in max norm and 3e-3 in relative L2 (fp32 summation order)."""
     from neo360_b200 import training
     net, sc, P, rays, (W, H, nc, nf) = _tiny(cuda)
+    net.train_projected = projected
     Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
     maps = {k: sc[k].clone().requires_grad_(True) for k in ("planes_xz", "planes_xy", "planes_yz", "latent")}
     osc = orc.Scene(maps["planes_xz"], maps["planes_xy"], maps["planes_yz"], maps["latent"], sc["src_poses"],
@@ -121,17 +125,22 @@ def test_training_forward_and_gradients_vs_oracle(cuda):
         for a, b in zip(got[lvl], ref[lvl]):
             assert md(a, b) < 2e-4, (lvl, md(a, b))
     training.training_loss(got, target.to(cuda)).backward()
-    worst = 0.0
+    # two measures per tensor: max |error| against the tensor's gradient scale (re-association noise of fp32 sums over ~1e5 point-views:
+    # scatter-add atomics, GPU vs CPU GEMM order; bound 1e-2) and the relative L2 error of the whole tensor (bound 3e-3)
+    rel2 = lambda a, b: float((a.detach().cpu().double() - b.detach().cpu().double()).norm() / max(float(b.detach().cpu().double().norm()), 1e-30))
+    worst, worst2 = 0.0, 0.0
     for name, p in net.named_parameters():
         gref = Pg[name].grad
         scale = float(gref.abs().max())
-        err = md(p.grad, gref)
-        worst = max(worst, err / max(scale, 1e-12))
-        assert err < 5e-3 * scale + 1e-9, (name, err, scale)
+        err, e2 = md(p.grad, gref), rel2(p.grad, gref)
+        worst, worst2 = max(worst, err / max(scale, 1e-12)), max(worst2, e2)
+        assert err < 1e-2 * scale + 1e-9 and e2 < 3e-3, (name, err, scale, e2)
     for k in maps:
         scale = float(maps[k].grad.abs().max())
-        assert md(dmaps[k].grad, maps[k].grad) < 5e-3 * scale + 1e-9, (k, md(dmaps[k].grad, maps[k].grad), scale)
-    print("worst relative parameter-gradient error", worst)
+        err, e2 = md(dmaps[k].grad, maps[k].grad), rel2(dmaps[k].grad, maps[k].grad)
+        worst, worst2 = max(worst, err / max(scale, 1e-12)), max(worst2, e2)
+        assert err < 1e-2 * scale + 1e-9 and e2 < 3e-3, (k, err, scale, e2)
+    print(f"projected={projected}: worst max-abs gradient error / scale {worst:.2e}, worst relative L2 {worst2:.2e}")
 
 
 def _worker(rank, world, port, q):
