@@ -159,6 +159,7 @@ class NeRF_TP(nn.Module):
             L.check(lib.neo_scene_create(C.byref(d), arr, mask, C.byref(h), torch.cuda.current_stream().cuda_stream))
         self._scene = Scene(h, lib.neo_scene_bytes(h))
         self._scene.nv = nv
+        self._scene.mask = mask
         self._param_key = self._params_version()
         self._scene_src = None
         return self._scene
@@ -189,11 +190,16 @@ class NeRF_TP(nn.Module):
                 self._scene_src = (keyed, tuple(t._version for t in keyed))
         if self._scene is None:
             raise RuntimeError("no scene: call set_scene(...) or pass planes_*/latent in `rays`, or give an encoder")
-        if self._param_key != self._params_version():
-            # the packed weights (fp32 transposes, TMEM image, W0/W3-projected feature maps) are stale: re-pack from the kept inputs
+        need = 1 << PRECISIONS[self.precision]
+        if self._param_key != self._params_version() or not (self._scene.mask & need):
+            # the packed weights (fp32 transposes, TMEM image, W0/W3-projected feature maps) are stale, or the scene was last built for
+            # another use (a training step leaves a cameras-only scene): re-pack from the kept inputs
             src = self._scene_src
             a = self._scene_inputs
-            self.set_scene(*a[:8], precisions=a[8])
+            prec = a[8]
+            if prec is not None and not any(PRECISIONS[p] == PRECISIONS[self.precision] for p in prec):
+                prec = list(prec) + [self.precision]
+            self.set_scene(*a[:8], precisions=prec)
             self._scene_src = src
         return self._scene
 

@@ -143,6 +143,32 @@ def test_training_forward_and_gradients_vs_oracle(cuda, projected):
     print(f"projected={projected}: worst max-abs gradient error / scale {worst:.2e}, worst relative L2 {worst2:.2e}")
 
 
+@pytest.mark.gpu
+def test_render_after_a_training_step_repacks_the_scene(cuda):
+    """A training step leaves a cameras-only scene behind (projected formulation) and changes the weights: the next eval call on the same
+    `set_scene` inputs must re-pack the scene for rendering and use the NEW weights (against the oracle, fp32 path, 2e-4)."""
+    from neo360_b200 import training
+    net, sc, P, rays, (W, H, nc, nf) = _tiny(cuda)
+    dev_sc = [sc[k].to(cuda) for k in ("planes_xz", "planes_xy", "planes_yz", "latent", "src_poses", "src_focal", "src_c")]
+    net.set_scene(*dev_sc, sc["img_wh"])
+    batch = {k: v.to(cuda) for k, v in rays.items()}
+    target = torch.rand(rays["rays_o"].shape[0], 3, generator=torch.Generator().manual_seed(3)).to(cuda)
+    opt = torch.optim.SGD([p for m in net._mlps() for p in m.parameters()], lr=5e-2)
+    loss = training.training_loss(net(batch, False, False, None, None, out_depth=False), target)
+    loss.backward()
+    opt.step()
+    assert net._scene.mask == 0                                  # what the training step left
+    net.eval()
+    with torch.no_grad():
+        got = net(batch, False, False, None, None, out_depth=True)[1]
+    net.check()
+    P2 = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    osc = orc.Scene(sc["planes_xz"], sc["planes_xy"], sc["planes_yz"], sc["latent"], sc["src_poses"],
+                    float(sc["src_focal"][0]), float(sc["src_c"][0, 0]), float(sc["src_c"][0, 1]), W, H)
+    ref = orc.render(rays, osc, P2, nc, nf, False, True)[1]
+    assert md(got[0], ref[0]) < 2e-4 and md(got[0], orc.render(rays, osc, P, nc, nf, False, True)[1][0]) > 1e-6
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
