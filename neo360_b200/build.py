@@ -26,11 +26,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libneo360_b200.so must be prebuilt")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = f"{LIB}.{os.getpid()}.tmp"      # per process: ranks that decide to build at the same time do not write into each other's file
+    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB + ".tmp", LIB)   # atomic: a concurrent reader never sees a half-written library
+    os.replace(tmp, LIB)   # atomic: a concurrent reader never sees a half-written library
     if verbose:
         print(res.stderr)
     return LIB
